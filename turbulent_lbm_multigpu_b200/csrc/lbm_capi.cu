@@ -1,0 +1,761 @@
+/*
+ * lbm_capi.cu -- host side of liblbm_b200.so: the C ABI of include/lbm_b200.h over the CUDA
+ * runtime.  Replaces the reference's OpenCL plumbing (src/libcl/CCL.hpp) and the bodies of
+ * CLbmSolver<T> (src/CLbmSolver.hpp); see the header for the per-entry-point mapping.
+ * There is deliberately no CPU fallback: without a CUDA device lbmCreate fails.
+ */
+#include "lbm_kernels.cuh"
+#include "../../include/lbm_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lbm;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Box { int x0, nx, y0, ny, z0, nz; };
+
+} // namespace
+
+struct lbm_solver {
+	lbm_desc desc;
+	int device;
+	int dtype;
+	int sx, sy, sz;
+	long long n;
+	size_t elem;                 /* sizeof(T) */
+	void *dd, *velocity, *density;
+	int *flags;
+	void *staging; size_t staging_bytes;
+	double *d_checksum;
+	cudaStream_t compute, comm;
+	bool own_compute, own_comm;
+	cudaEvent_t ev_compute, ev_comm, ev_t0, ev_t1;
+	uint64_t counter;
+	uint64_t launches;
+	int vec;
+	int block;
+	int wg_quirk;                /* >0 only when the work-group x-shift is observable */
+	bool smag;
+	double u_lid;
+	std::string error;
+};
+
+namespace {
+
+int fail(lbm_t h, int code, const std::string &msg)
+{
+	if (h) h->error = msg;
+	g_last_error = msg;
+	return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                     \
+	do {                                                                                      \
+		cudaError_t e__ = (expr);                                                             \
+		if (e__ != cudaSuccess)                                                               \
+			return fail((h), LBM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+	} while (0)
+
+#define CHECK_HANDLE(h) \
+	do { if (!(h)) return fail(NULL, LBM_ERR_INVALID, "null handle"); } while (0)
+
+int use_device(lbm_t h) { CUDA_TRY(h, cudaSetDevice(h->device)); return LBM_OK; }
+
+template <typename T>
+StepParams<T> make_params(lbm_t h, const Box &b)
+{
+	StepParams<T> P;
+	P.dd = (T *)h->dd; P.flags = h->flags; P.velocity = (T *)h->velocity; P.density = (T *)h->density;
+	P.n = h->n; P.sx = h->sx; P.sy = h->sy; P.sz = h->sz; P.sxy = (long long)h->sx * h->sy;
+	P.inv_tau = (T)h->desc.inv_tau; P.tau = (T)h->desc.tau;
+	/* smag_k = 18*sqrt(2)*C_s^2 evaluated in double, rounded once to T (oracle/port.py) */
+	P.smag_k = (T)(18.0 * std::sqrt(2.0) * h->desc.smagorinsky_cs * h->desc.smagorinsky_cs);
+	P.gx = (T)h->desc.gravitation[0]; P.gy = (T)h->desc.gravitation[1]; P.gz = (T)h->desc.gravitation[2];
+	P.u_lid = (T)h->u_lid;
+	P.x0 = b.x0; P.nx = b.nx; P.y0 = b.y0; P.ny = b.ny; P.z0 = b.z0; P.nz = b.nz;
+	P.wg = h->wg_quirk;
+	P.store_v = h->desc.store_velocity; P.store_r = h->desc.store_density;
+	return P;
+}
+
+template <typename T, int VEC, bool SMAG, bool STORE>
+void launch_alpha(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStream_t s)
+{
+	lbm_alpha_kernel<T, VEC, SMAG, STORE><<<grid, block, 0, s>>>(P);
+}
+
+template <typename T, int VEC, bool SMAG, bool STORE>
+void launch_beta(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStream_t s)
+{
+	if (h->desc.beta_order == LBM_BETA_ORDER_SHIPPED)
+		lbm_beta_kernel<T, VEC, SMAG, STORE, 0><<<grid, block, 0, s>>>(P);
+	else
+		lbm_beta_kernel<T, VEC, SMAG, STORE, 1><<<grid, block, 0, s>>>(P);
+}
+
+template <typename T, int VEC>
+int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s)
+{
+	if (b.nx <= 0 || b.ny <= 0 || b.nz <= 0) return LBM_OK;
+	const StepParams<T> P = make_params<T>(h, b);
+	const long long groups = ((long long)b.nx * b.ny) / VEC;
+	dim3 block(h->block);
+	dim3 grid((unsigned)((groups + h->block - 1) / h->block), (unsigned)b.nz);
+	const bool store = h->desc.store_velocity || h->desc.store_density;
+#define LBM_DISPATCH(FN)                                              \
+	do {                                                              \
+		if (h->smag) { if (store) FN<T, VEC, true, true>(h, P, grid, block, s);   \
+		               else       FN<T, VEC, true, false>(h, P, grid, block, s); }\
+		else         { if (store) FN<T, VEC, false, true>(h, P, grid, block, s);  \
+		               else       FN<T, VEC, false, false>(h, P, grid, block, s); } \
+	} while (0)
+	if (alpha) LBM_DISPATCH(launch_alpha); else LBM_DISPATCH(launch_beta);
+#undef LBM_DISPATCH
+	h->launches++;
+	CUDA_TRY(h, cudaGetLastError());
+	return LBM_OK;
+}
+
+int launch_step(lbm_t h, bool alpha, const Box &b, cudaStream_t s)
+{
+	if (h->dtype == LBM_F32) {
+		switch (h->vec) {
+		case 4: return launch_step_tv<float, 4>(h, alpha, b, s);
+		case 2: return launch_step_tv<float, 2>(h, alpha, b, s);
+		default: return launch_step_tv<float, 1>(h, alpha, b, s);
+		}
+	}
+	switch (h->vec) {
+	case 2: return launch_step_tv<double, 2>(h, alpha, b, s);
+	default: return launch_step_tv<double, 1>(h, alpha, b, s);
+	}
+}
+
+Box full_box(lbm_t h) { Box b = { 0, h->sx, 0, h->sy, 0, h->sz }; return b; }
+
+/*
+ * Partition of the sub-domain for communication/computation overlap: the shell is every
+ * cell within the two outermost layers of a face that has a neighbour (x faces: XS cells so
+ * that whole vectors/warps stay coalesced), cut into disjoint boxes; the interior is the rest.
+ * ghost_faces bit (axis*2 + side).
+ */
+void partition(lbm_t h, int ghost_faces, std::vector<Box> &shell, Box &interior)
+{
+	const int S[3] = { h->sx, h->sy, h->sz };
+	int lo[3], hi[3];
+	for (int a = 0; a < 3; a++) {
+		int t = 2;
+		if (a == 0) { t = 32; while (t > 2 && (t > S[0] / 4 || (S[0] % t) != 0)) t >>= 1; if (t < h->vec) t = h->vec; }
+		lo[a] = (ghost_faces >> (2 * a)) & 1 ? t : 0;
+		hi[a] = (ghost_faces >> (2 * a + 1)) & 1 ? S[a] - t : S[a];
+		if (lo[a] > hi[a]) { lo[a] = 0; hi[a] = 0; }   /* everything is shell */
+	}
+	shell.clear();
+	/* z shells: full x,y */
+	if (lo[2] > 0) shell.push_back(Box{ 0, S[0], 0, S[1], 0, lo[2] });
+	if (hi[2] < S[2]) shell.push_back(Box{ 0, S[0], 0, S[1], hi[2], S[2] - hi[2] });
+	const int z0 = lo[2], nz = hi[2] - lo[2];
+	/* y shells: full x, interior z */
+	if (lo[1] > 0) shell.push_back(Box{ 0, S[0], 0, lo[1], z0, nz });
+	if (hi[1] < S[1]) shell.push_back(Box{ 0, S[0], hi[1], S[1] - hi[1], z0, nz });
+	const int y0 = lo[1], ny = hi[1] - lo[1];
+	/* x shells: interior y,z */
+	if (lo[0] > 0) shell.push_back(Box{ 0, lo[0], y0, ny, z0, nz });
+	if (hi[0] < S[0]) shell.push_back(Box{ hi[0], S[0] - hi[0], y0, ny, z0, nz });
+	interior = Box{ lo[0], hi[0] - lo[0], y0, ny, z0, nz };
+}
+
+int ensure_staging(lbm_t h, size_t bytes)
+{
+	if (bytes <= h->staging_bytes) return LBM_OK;
+	if (h->staging) { CUDA_TRY(h, cudaFree(h->staging)); h->staging = NULL; h->staging_bytes = 0; }
+	CUDA_TRY(h, cudaMalloc(&h->staging, bytes));
+	h->staging_bytes = bytes;
+	return LBM_OK;
+}
+
+int ensure_field(lbm_t h, void **buf, int comps)
+{
+	if (*buf) return LBM_OK;
+	const size_t bytes = (size_t)comps * h->n * h->elem;
+	CUDA_TRY(h, cudaMalloc(buf, bytes));
+	CUDA_TRY(h, cudaMemsetAsync(*buf, 0, bytes, h->compute));
+	return LBM_OK;
+}
+
+int check_rect(lbm_t h, const int origin[3], const int size[3])
+{
+	const int S[3] = { h->sx, h->sy, h->sz };
+	for (int a = 0; a < 3; a++)
+		if (origin[a] < 0 || size[a] <= 0 || origin[a] + size[a] > S[a])
+			return fail(h, LBM_ERR_INVALID, "rect outside the sub-domain");
+	return LBM_OK;
+}
+
+template <typename T>
+void launch_rect(lbm_t h, const T *src, T *dst, const RectCopy &R, cudaStream_t s)
+{
+	const long long total = (long long)R.block[0] * R.block[1] * R.block[2] * R.ncomp;
+	const int block = 256;
+	long long grid = (total + block - 1) / block;
+	if (grid > 148LL * 16) grid = 148LL * 16;
+	if (grid < 1) grid = 1;
+	rect_copy_kernel<T><<<(unsigned)grid, block, 0, s>>>(src, dst, R);
+	h->launches++;
+}
+
+void launch_rect_bytes(lbm_t h, size_t elem, const void *src, void *dst, const RectCopy &R, cudaStream_t s)
+{
+	if (elem == 4) launch_rect<float>(h, (const float *)src, (float *)dst, R, s);
+	else launch_rect<double>(h, (const double *)src, (double *)dst, R, s);
+}
+
+/* field (ncomp_total components of n cells) rect  <->  packed buffer [comp][z][y][x] */
+RectCopy rect_desc(lbm_t h, const int origin[3], const int size[3], bool to_packed,
+		const int *field_comps, const int *packed_comps, int ncomp)
+{
+	RectCopy R;
+	const long long cells = (long long)size[0] * size[1] * size[2];
+	const int zero[3] = { 0, 0, 0 };
+	const int S[3] = { h->sx, h->sy, h->sz };
+	for (int a = 0; a < 3; a++) {
+		R.block[a] = size[a];
+		R.so[a] = to_packed ? origin[a] : zero[a];
+		R.ss[a] = to_packed ? S[a] : size[a];
+		R.dorg[a] = to_packed ? zero[a] : origin[a];
+		R.ds[a] = to_packed ? size[a] : S[a];
+	}
+	R.src_comp_stride = to_packed ? h->n : cells;
+	R.dst_comp_stride = to_packed ? cells : h->n;
+	R.ncomp = ncomp;
+	for (int c = 0; c < ncomp; c++) {
+		R.src_comp[c] = to_packed ? field_comps[c] : packed_comps[c];
+		R.dst_comp[c] = to_packed ? packed_comps[c] : field_comps[c];
+	}
+	return R;
+}
+
+int store_field(lbm_t h, const void *field, size_t elem, int comps, void *host_dst,
+		const int origin[3], const int size[3])
+{
+	if (int rc = use_device(h)) return rc;
+	if (!host_dst) return fail(h, LBM_ERR_INVALID, "null host pointer");
+	if (!origin || !size) {
+		CUDA_TRY(h, cudaMemcpyAsync(host_dst, field, (size_t)comps * h->n * elem, cudaMemcpyDeviceToHost, h->compute));
+		CUDA_TRY(h, cudaStreamSynchronize(h->compute));
+		return LBM_OK;
+	}
+	if (int rc = check_rect(h, origin, size)) return rc;
+	const size_t bytes = (size_t)comps * size[0] * size[1] * size[2] * elem;
+	if (int rc = ensure_staging(h, bytes)) return rc;
+	int ids[19];
+	for (int c = 0; c < comps; c++) ids[c] = c;
+	const RectCopy R = rect_desc(h, origin, size, true, ids, ids, comps);
+	launch_rect_bytes(h, elem, field, h->staging, R, h->compute);
+	CUDA_TRY(h, cudaGetLastError());
+	CUDA_TRY(h, cudaMemcpyAsync(host_dst, h->staging, bytes, cudaMemcpyDeviceToHost, h->compute));
+	CUDA_TRY(h, cudaStreamSynchronize(h->compute));
+	return LBM_OK;
+}
+
+int set_field(lbm_t h, void *field, size_t elem, int comps, const void *host_src,
+		const int origin[3], const int size[3], const int *keep /* per component or NULL */)
+{
+	if (int rc = use_device(h)) return rc;
+	if (!host_src) return fail(h, LBM_ERR_INVALID, "null host pointer");
+	if (!origin || !size) {
+		CUDA_TRY(h, cudaMemcpyAsync(field, host_src, (size_t)comps * h->n * elem, cudaMemcpyHostToDevice, h->compute));
+		CUDA_TRY(h, cudaStreamSynchronize(h->compute));
+		return LBM_OK;
+	}
+	if (int rc = check_rect(h, origin, size)) return rc;
+	const size_t bytes = (size_t)comps * size[0] * size[1] * size[2] * elem;
+	if (int rc = ensure_staging(h, bytes)) return rc;
+	CUDA_TRY(h, cudaMemcpyAsync(h->staging, host_src, bytes, cudaMemcpyHostToDevice, h->compute));
+	int ids[19], nsel = 0;
+	for (int c = 0; c < comps; c++) if (!keep || keep[c]) ids[nsel++] = c;
+	if (nsel > 0) {
+		const RectCopy R = rect_desc(h, origin, size, false, ids, ids, nsel);
+		launch_rect_bytes(h, elem, h->staging, field, R, h->compute);
+		CUDA_TRY(h, cudaGetLastError());
+	}
+	/* the host buffer is consumed before return (CL_MEM_COPY_HOST_PTR semantics) */
+	CUDA_TRY(h, cudaStreamSynchronize(h->compute));
+	return LBM_OK;
+}
+
+const int kUnits[19][3] = {
+	{ 1, 0, 0 }, { -1, 0, 0 }, { 0, 1, 0 }, { 0, -1, 0 },
+	{ 1, 1, 0 }, { -1, -1, 0 }, { 1, -1, 0 }, { -1, 1, 0 },
+	{ 1, 0, 1 }, { -1, 0, -1 }, { 1, 0, -1 }, { -1, 0, 1 },
+	{ 0, 1, 1 }, { 0, -1, -1 }, { 0, 1, -1 }, { 0, -1, 1 },
+	{ 0, 0, 1 }, { 0, 0, -1 }, { 0, 0, 0 } };
+
+int popcount19(uint32_t m) { int c = 0; for (int f = 0; f < 19; f++) c += (m >> f) & 1; return c; }
+
+} // namespace
+
+/* ====================================================================== C ABI */
+extern "C" {
+
+int lbmGetVersion(void) { return 100; }
+
+const char *lbmGetLastErrorString(lbm_t h) { return h ? h->error.c_str() : g_last_error.c_str(); }
+
+int lbmGetDeviceCount(int *count)
+{
+	if (!count) return fail(NULL, LBM_ERR_INVALID, "null count");
+	int c = 0;
+	cudaError_t e = cudaGetDeviceCount(&c);
+	if (e != cudaSuccess) { *count = 0; return fail(NULL, LBM_ERR_NO_DEVICE, cudaGetErrorString(e)); }
+	*count = c;
+	return LBM_OK;
+}
+
+int lbmCreate(lbm_t *out, const lbm_desc *d)
+{
+	if (!out || !d) return fail(NULL, LBM_ERR_INVALID, "null argument");
+	*out = NULL;
+	if (d->struct_size != sizeof(lbm_desc)) return fail(NULL, LBM_ERR_INVALID, "lbm_desc.struct_size mismatch");
+	if (d->dtype != LBM_F32 && d->dtype != LBM_F64) return fail(NULL, LBM_ERR_INVALID, "unsupported class type T");
+	for (int a = 0; a < 3; a++) if (d->size[a] < 1) return fail(NULL, LBM_ERR_INVALID, "domain size must be positive");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return fail(NULL, LBM_ERR_NO_DEVICE, "no CUDA device available (liblbm_b200 has no CPU fallback)");
+	if (d->device < 0 || d->device >= ndev) return fail(NULL, LBM_ERR_INVALID, "invalid device number");
+
+	lbm_solver *h = new lbm_solver();
+	h->desc = *d;
+	h->device = d->device; h->dtype = d->dtype;
+	h->sx = d->size[0]; h->sy = d->size[1]; h->sz = d->size[2];
+	h->n = (long long)h->sx * h->sy * h->sz;
+	h->elem = d->dtype == LBM_F32 ? 4 : 8;
+	h->dd = h->velocity = h->density = NULL; h->flags = NULL;
+	h->staging = NULL; h->staging_bytes = 0; h->d_checksum = NULL;
+	h->counter = 0; h->launches = 0;
+	h->smag = d->smagorinsky_cs != 0.0;
+	h->u_lid = d->u_lid;
+	const int maxvec = d->dtype == LBM_F32 ? 4 : 2;
+	int vec = d->vector_width > 0 ? d->vector_width : maxvec;
+	if (vec > maxvec) vec = maxvec;
+	while (vec > 1 && (h->sx % vec) != 0) vec >>= 1;
+	if (vec != 1 && vec != 2 && vec != 4) vec = 1;
+	h->vec = vec;
+	h->block = d->block_size > 0 ? d->block_size : 128;
+	if (h->block % 32 != 0 || h->block > 1024) { delete h; return fail(NULL, LBM_ERR_INVALID, "block_size must be a multiple of 32 and <= 1024"); }
+	const int wg = d->work_group_size;
+	h->wg_quirk = (wg > 0 && d->beta_order == LBM_BETA_ORDER_SHIPPED && (wg % h->sx) == 0 && (h->n % wg) == 0) ? wg : 0;
+
+#define CREATE_TRY(expr)                                                                     \
+	do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) {                                  \
+		std::string m = std::string(#expr) + ": " + cudaGetErrorString(e__);                  \
+		lbmDestroy(h); return fail(NULL, LBM_ERR_CUDA, m); } } while (0)
+	CREATE_TRY(cudaSetDevice(h->device));
+	h->own_compute = d->compute_stream == NULL; h->own_comm = d->comm_stream == NULL;
+	h->compute = (cudaStream_t)d->compute_stream; h->comm = (cudaStream_t)d->comm_stream;
+	if (h->own_compute) CREATE_TRY(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+	if (h->own_comm) CREATE_TRY(cudaStreamCreateWithFlags(&h->comm, cudaStreamNonBlocking));
+	CREATE_TRY(cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreate(&h->ev_t0));
+	CREATE_TRY(cudaEventCreate(&h->ev_t1));
+	CREATE_TRY(cudaMalloc(&h->dd, (size_t)19 * h->n * h->elem));
+	CREATE_TRY(cudaMalloc((void **)&h->flags, (size_t)h->n * sizeof(int)));
+	CREATE_TRY(cudaMalloc((void **)&h->d_checksum, sizeof(double)));
+	if (d->store_velocity) { CREATE_TRY(cudaMalloc(&h->velocity, (size_t)3 * h->n * h->elem)); }
+	if (d->store_density) { CREATE_TRY(cudaMalloc(&h->density, (size_t)h->n * h->elem)); }
+#undef CREATE_TRY
+	*out = h;
+	int rc = lbmReset(h);
+	if (rc != LBM_OK) { std::string m = h->error; lbmDestroy(h); *out = NULL; return fail(NULL, rc, m); }
+	return LBM_OK;
+}
+
+int lbmDestroy(lbm_t h)
+{
+	if (!h) return LBM_OK;
+	cudaSetDevice(h->device);
+	if (h->compute) cudaStreamSynchronize(h->compute);
+	if (h->comm) cudaStreamSynchronize(h->comm);
+	cudaFree(h->dd); cudaFree(h->flags); cudaFree(h->velocity); cudaFree(h->density);
+	cudaFree(h->staging); cudaFree(h->d_checksum);
+	if (h->ev_compute) cudaEventDestroy(h->ev_compute);
+	if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+	if (h->own_compute && h->compute) cudaStreamDestroy(h->compute);
+	if (h->own_comm && h->comm) cudaStreamDestroy(h->comm);
+	delete h;
+	return LBM_OK;
+}
+
+int lbmReset(lbm_t h)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	h->counter = 0;
+	const int block = 256;
+	const unsigned grid = (unsigned)((h->n + block - 1) / block);
+	const int *bc = h->desc.bc;
+	if (h->dtype == LBM_F32)
+		lbm_init_kernel<float><<<grid, block, 0, h->compute>>>((float *)h->dd, h->flags, (float *)h->velocity,
+				(float *)h->density, h->n, h->sx, h->sy, h->sz, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5],
+				h->velocity != NULL, h->density != NULL);
+	else
+		lbm_init_kernel<double><<<grid, block, 0, h->compute>>>((double *)h->dd, h->flags, (double *)h->velocity,
+				(double *)h->density, h->n, h->sx, h->sy, h->sz, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5],
+				h->velocity != NULL, h->density != NULL);
+	h->launches++;
+	CUDA_TRY(h, cudaGetLastError());
+	return LBM_OK;
+}
+
+int lbmStepAlpha(lbm_t h)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	return launch_step(h, true, full_box(h), h->compute);
+}
+
+int lbmStepBeta(lbm_t h)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	return launch_step(h, false, full_box(h), h->compute);
+}
+
+int lbmStep(lbm_t h)
+{
+	CHECK_HANDLE(h);
+	/* CLbmSolver::simulationStep, src/CLbmSolver.hpp:664-676 */
+	int rc = (h->counter & 1) ? lbmStepAlpha(h) : lbmStepBeta(h);
+	if (rc == LBM_OK) h->counter++;
+	return rc;
+}
+
+int lbmSteps(lbm_t h, int nsteps)
+{
+	CHECK_HANDLE(h);
+	for (int i = 0; i < nsteps; i++)
+		if (int rc = lbmStep(h)) return rc;
+	return LBM_OK;
+}
+
+int lbmStepShell(lbm_t h, int ghost_faces)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	std::vector<Box> shell; Box interior;
+	partition(h, ghost_faces, shell, interior);
+	const bool alpha = (h->counter & 1) != 0;
+	for (size_t i = 0; i < shell.size(); i++)
+		if (int rc = launch_step(h, alpha, shell[i], h->compute)) return rc;
+	return LBM_OK;
+}
+
+int lbmStepInterior(lbm_t h, int ghost_faces)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	std::vector<Box> shell; Box interior;
+	partition(h, ghost_faces, shell, interior);
+	const bool alpha = (h->counter & 1) != 0;
+	if (int rc = launch_step(h, alpha, interior, h->compute)) return rc;
+	h->counter++;
+	return LBM_OK;
+}
+
+int lbmStreamWaitStream(lbm_t h, int waiter_is_comm)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	if (waiter_is_comm) {
+		CUDA_TRY(h, cudaEventRecord(h->ev_compute, h->compute));
+		CUDA_TRY(h, cudaStreamWaitEvent(h->comm, h->ev_compute, 0));
+	} else {
+		CUDA_TRY(h, cudaEventRecord(h->ev_comm, h->comm));
+		CUDA_TRY(h, cudaStreamWaitEvent(h->compute, h->ev_comm, 0));
+	}
+	return LBM_OK;
+}
+
+int lbmGetStreams(lbm_t h, void **compute_stream, void **comm_stream)
+{
+	CHECK_HANDLE(h);
+	if (compute_stream) *compute_stream = (void *)h->compute;
+	if (comm_stream) *comm_stream = (void *)h->comm;
+	return LBM_OK;
+}
+
+int lbmWait(lbm_t h)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	CUDA_TRY(h, cudaStreamSynchronize(h->compute));
+	CUDA_TRY(h, cudaStreamSynchronize(h->comm));
+	return LBM_OK;
+}
+
+int lbmGetStepCounter(lbm_t h, uint64_t *counter)
+{
+	CHECK_HANDLE(h);
+	if (!counter) return fail(h, LBM_ERR_INVALID, "null counter");
+	*counter = h->counter;
+	return LBM_OK;
+}
+
+int lbmSetStepCounter(lbm_t h, uint64_t counter) { CHECK_HANDLE(h); h->counter = counter; return LBM_OK; }
+
+int lbmSetDrivenCavityVelocity(lbm_t h, double u_lid) { CHECK_HANDLE(h); h->u_lid = u_lid; return LBM_OK; }
+
+int lbmStoreDD(lbm_t h, void *host_dst, const int origin[3], const int size[3])
+{
+	CHECK_HANDLE(h);
+	return store_field(h, h->dd, h->elem, 19, host_dst, origin, size);
+}
+
+int lbmSetDD(lbm_t h, const void *host_src, const int origin[3], const int size[3], const int norm[3])
+{
+	CHECK_HANDLE(h);
+	int keep[19];
+	for (int f = 0; f < 19; f++)   /* src/CLbmSolver.hpp:748: norm.dotProd(lbm_units[f]) > 0 */
+		keep[f] = !norm || (norm[0] * kUnits[f][0] + norm[1] * kUnits[f][1] + norm[2] * kUnits[f][2] > 0);
+	return set_field(h, h->dd, h->elem, 19, host_src, origin, size, keep);
+}
+
+int lbmStoreVelocity(lbm_t h, void *host_dst, const int origin[3], const int size[3])
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	if (int rc = ensure_field(h, &h->velocity, 3)) return rc;
+	return store_field(h, h->velocity, h->elem, 3, host_dst, origin, size);
+}
+
+int lbmSetVelocity(lbm_t h, const void *host_src, const int origin[3], const int size[3])
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	if (int rc = ensure_field(h, &h->velocity, 3)) return rc;
+	return set_field(h, h->velocity, h->elem, 3, host_src, origin, size, NULL);
+}
+
+int lbmStoreDensity(lbm_t h, void *host_dst, const int origin[3], const int size[3])
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	if (int rc = ensure_field(h, &h->density, 1)) return rc;
+	return store_field(h, h->density, h->elem, 1, host_dst, origin, size);
+}
+
+int lbmSetDensity(lbm_t h, const void *host_src, const int origin[3], const int size[3])
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	if (int rc = ensure_field(h, &h->density, 1)) return rc;
+	return set_field(h, h->density, h->elem, 1, host_src, origin, size, NULL);
+}
+
+int lbmStoreFlags(lbm_t h, int *host_dst, const int origin[3], const int size[3])
+{
+	CHECK_HANDLE(h);
+	return store_field(h, h->flags, sizeof(int), 1, host_dst, origin, size);
+}
+
+int lbmSetFlags(lbm_t h, const int *host_src, const int origin[3], const int size[3])
+{
+	CHECK_HANDLE(h);
+	return set_field(h, h->flags, sizeof(int), 1, host_src, origin, size, NULL);
+}
+
+int lbmChecksumVelocity(lbm_t h, double *out, int host_order)
+{
+	CHECK_HANDLE(h);
+	if (!out) return fail(h, LBM_ERR_INVALID, "null out");
+	if (int rc = use_device(h)) return rc;
+	if (int rc = ensure_field(h, &h->velocity, 3)) return rc;
+	if (host_order) {
+		/* src/CLbmSolver.hpp:1103-1123 verbatim semantics: float accumulator, index order */
+		std::vector<char> vel((size_t)3 * h->n * h->elem);
+		std::vector<int> fl((size_t)h->n);
+		if (int rc = store_field(h, h->velocity, h->elem, 3, vel.data(), NULL, NULL)) return rc;
+		if (int rc = store_field(h, h->flags, sizeof(int), 1, fl.data(), NULL, NULL)) return rc;
+		float checksum = 0;
+		if (h->dtype == LBM_F32) {
+			const float *v = (const float *)vel.data();
+			for (long long a = 0; a < h->n; a++)
+				if (fl[a] == LBM_FLAG_FLUID) checksum += v[a] + v[h->n + a] + v[2 * h->n + a];
+		} else {
+			const double *v = (const double *)vel.data();
+			for (long long a = 0; a < h->n; a++)
+				if (fl[a] == LBM_FLAG_FLUID) checksum += v[a] + v[h->n + a] + v[2 * h->n + a];
+		}
+		*out = checksum;
+		return LBM_OK;
+	}
+	CUDA_TRY(h, cudaMemsetAsync(h->d_checksum, 0, sizeof(double), h->compute));
+	const int block = 256, grid = 148 * 8;
+	if (h->dtype == LBM_F32)
+		checksum_kernel<float><<<grid, block, 0, h->compute>>>((const float *)h->velocity, h->flags, h->n, h->d_checksum);
+	else
+		checksum_kernel<double><<<grid, block, 0, h->compute>>>((const double *)h->velocity, h->flags, h->n, h->d_checksum);
+	h->launches++;
+	CUDA_TRY(h, cudaGetLastError());
+	CUDA_TRY(h, cudaMemcpyAsync(out, h->d_checksum, sizeof(double), cudaMemcpyDeviceToHost, h->compute));
+	CUDA_TRY(h, cudaStreamSynchronize(h->compute));
+	return LBM_OK;
+}
+
+/* ---------------------------------------------------------------- halo path */
+int lbmHaloSlotMask(int sync_kind, const int recv_dir[3], int slots, uint32_t *mask)
+{
+	if (!mask || !recv_dir) return fail(NULL, LBM_ERR_INVALID, "null argument");
+	uint32_t m = 0;
+	for (int f = 0; f < 19; f++) {
+		const int dot = recv_dir[0] * kUnits[f][0] + recv_dir[1] * kUnits[f][1] + recv_dir[2] * kUnits[f][2];
+		bool keep;
+		if (sync_kind == LBM_SYNC_BETA) keep = dot > 0;            /* src/CLbmSolver.hpp:748 */
+		else keep = (slots == LBM_HALO_SLOTS_MINIMAL) ? (dot < 0) : true;
+		if (keep) m |= 1u << f;
+	}
+	*mask = m;
+	return LBM_OK;
+}
+
+int lbmHaloBytes(lbm_t h, const int size[3], uint32_t slot_mask, size_t *bytes)
+{
+	CHECK_HANDLE(h);
+	if (!size || !bytes) return fail(h, LBM_ERR_INVALID, "null argument");
+	*bytes = (size_t)popcount19(slot_mask) * size[0] * size[1] * size[2] * h->elem;
+	return LBM_OK;
+}
+
+int lbmHaloPack(lbm_t h, const int origin[3], const int size[3], uint32_t slot_mask, void *dev_buf, void *stream)
+{
+	CHECK_HANDLE(h);
+	if (!origin || !size || !dev_buf) return fail(h, LBM_ERR_INVALID, "null argument");
+	if (int rc = use_device(h)) return rc;
+	if (int rc = check_rect(h, origin, size)) return rc;
+	int field[19], packed[19], n = 0;
+	for (int f = 0; f < 19; f++) if ((slot_mask >> f) & 1) { field[n] = f; packed[n] = n; n++; }
+	if (n == 0) return LBM_OK;
+	const RectCopy R = rect_desc(h, origin, size, true, field, packed, n);
+	launch_rect_bytes(h, h->elem, h->dd, dev_buf, R, stream ? (cudaStream_t)stream : h->comm);
+	CUDA_TRY(h, cudaGetLastError());
+	return LBM_OK;
+}
+
+int lbmHaloUnpack(lbm_t h, const int origin[3], const int size[3], uint32_t buf_slot_mask, uint32_t write_mask,
+		const void *dev_buf, void *stream)
+{
+	CHECK_HANDLE(h);
+	if (!origin || !size || !dev_buf) return fail(h, LBM_ERR_INVALID, "null argument");
+	if (write_mask & ~buf_slot_mask) return fail(h, LBM_ERR_INVALID, "write_mask selects slots the buffer does not hold");
+	if (int rc = use_device(h)) return rc;
+	if (int rc = check_rect(h, origin, size)) return rc;
+	int field[19], packed[19], n = 0, pos = 0;
+	for (int f = 0; f < 19; f++) {
+		if (!((buf_slot_mask >> f) & 1)) continue;
+		if ((write_mask >> f) & 1) { field[n] = f; packed[n] = pos; n++; }
+		pos++;
+	}
+	if (n == 0) return LBM_OK;
+	const RectCopy R = rect_desc(h, origin, size, false, field, packed, n);
+	launch_rect_bytes(h, h->elem, dev_buf, h->dd, R, stream ? (cudaStream_t)stream : h->comm);
+	CUDA_TRY(h, cudaGetLastError());
+	return LBM_OK;
+}
+
+int lbmHaloCopyPeer(lbm_t src, const int src_origin[3], lbm_t dst, const int dst_origin[3],
+		const int size[3], uint32_t slot_mask, void *stream)
+{
+	CHECK_HANDLE(src); CHECK_HANDLE(dst);
+	if (!src_origin || !dst_origin || !size) return fail(src, LBM_ERR_INVALID, "null argument");
+	if (src->dtype != dst->dtype) return fail(src, LBM_ERR_INVALID, "peer dtype mismatch");
+	if (int rc = use_device(src)) return rc;
+	if (int rc = check_rect(src, src_origin, size)) return rc;
+	if (int rc = check_rect(dst, dst_origin, size)) return fail(src, rc, dst->error);
+	if (src->device != dst->device) {
+		int can = 0;
+		CUDA_TRY(src, cudaDeviceCanAccessPeer(&can, src->device, dst->device));
+		if (!can) return fail(src, LBM_ERR_CUDA, "devices are not NVLink/PCIe peers");
+		cudaError_t e = cudaDeviceEnablePeerAccess(dst->device, 0);
+		if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+			return fail(src, LBM_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+		cudaGetLastError();
+	}
+	RectCopy R;
+	const int S[3] = { src->sx, src->sy, src->sz }, D[3] = { dst->sx, dst->sy, dst->sz };
+	for (int a = 0; a < 3; a++) {
+		R.block[a] = size[a]; R.so[a] = src_origin[a]; R.ss[a] = S[a]; R.dorg[a] = dst_origin[a]; R.ds[a] = D[a];
+	}
+	R.src_comp_stride = src->n; R.dst_comp_stride = dst->n;
+	int n = 0;
+	for (int f = 0; f < 19; f++) if ((slot_mask >> f) & 1) { R.src_comp[n] = f; R.dst_comp[n] = f; n++; }
+	R.ncomp = n;
+	if (n == 0) return LBM_OK;
+	launch_rect_bytes(src, src->elem, src->dd, dst->dd, R, stream ? (cudaStream_t)stream : src->comm);
+	CUDA_TRY(src, cudaGetLastError());
+	return LBM_OK;
+}
+
+int lbmGetDevicePointer(lbm_t h, int which, void **ptr, size_t *bytes)
+{
+	CHECK_HANDLE(h);
+	if (!ptr) return fail(h, LBM_ERR_INVALID, "null ptr");
+	size_t b = 0;
+	switch (which) {
+	case LBM_BUF_DD: *ptr = h->dd; b = (size_t)19 * h->n * h->elem; break;
+	case LBM_BUF_FLAGS: *ptr = h->flags; b = (size_t)h->n * sizeof(int); break;
+	case LBM_BUF_VELOCITY: *ptr = h->velocity; b = h->velocity ? (size_t)3 * h->n * h->elem : 0; break;
+	case LBM_BUF_DENSITY: *ptr = h->density; b = h->density ? (size_t)h->n * h->elem : 0; break;
+	default: return fail(h, LBM_ERR_INVALID, "unknown buffer id");
+	}
+	if (bytes) *bytes = b;
+	return LBM_OK;
+}
+
+int lbmTimerStart(lbm_t h)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	CUDA_TRY(h, cudaEventRecord(h->ev_t0, h->compute));
+	return LBM_OK;
+}
+
+int lbmTimerStop(lbm_t h, float *milliseconds)
+{
+	CHECK_HANDLE(h);
+	if (!milliseconds) return fail(h, LBM_ERR_INVALID, "null milliseconds");
+	if (int rc = use_device(h)) return rc;
+	CUDA_TRY(h, cudaEventRecord(h->ev_t1, h->compute));
+	CUDA_TRY(h, cudaEventSynchronize(h->ev_t1));
+	CUDA_TRY(h, cudaEventElapsedTime(milliseconds, h->ev_t0, h->ev_t1));
+	return LBM_OK;
+}
+
+int lbmGetLaunchCount(lbm_t h, uint64_t *launches)
+{
+	CHECK_HANDLE(h);
+	if (!launches) return fail(h, LBM_ERR_INVALID, "null launches");
+	*launches = h->launches;
+	return LBM_OK;
+}
+
+int lbmGetConfig(lbm_t h, int *vector_width, int *block_size, int *wg_quirk)
+{
+	CHECK_HANDLE(h);
+	if (vector_width) *vector_width = h->vec;
+	if (block_size) *block_size = h->block;
+	if (wg_quirk) *wg_quirk = h->wg_quirk;
+	return LBM_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,683 @@
+/*
+ * lbm_kernels.cuh -- sm_100a device code of the D3Q19 alpha/beta time step.
+ *
+ * What the kernels compute is defined by the reference's OpenCL kernels
+ * (src/cl_programs/lbm_alpha.cl, lbm_beta.cl, lbm_init.cl, copy_buffer_rect.cl); HOW they
+ * compute it is B200-first:
+ *   - one thread owns VEC consecutive x cells (4 x fp32 / 2 x fp64 = 16 B): every slot whose
+ *     lattice vector has e_x = 0 (all 19 in alpha, 9 of 19 in beta) moves as one 128-bit
+ *     LDG/STG; the +-1 shifted slots of beta move as 32/64/32-bit pieces;
+ *   - no shared memory and no barriers: the reference's __local x-shift staging
+ *     (lbm_beta.cl:167-234, 7 barriers) exists to align loads on 2010 hardware; here the
+ *     L1/L2 absorb the one-element overlap between neighbouring threads and HBM traffic
+ *     stays at the algorithmic 2 x 19 values per cell;
+ *   - the periodic linear wrap and the work-group quirk only concern the outermost cells:
+ *     a block decides uniformly whether it needs the general (scalar, wrapping) path;
+ *   - floating-point expressions are written in the reference's operation order and the
+ *     translation unit is compiled with --fmad=false, so fp32/fp64 results are
+ *     bit-identical to the reference kernels executed in strict IEEE arithmetic.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lbm {
+
+enum : int { FLAG_OBSTACLE = 1, FLAG_FLUID = 2, FLAG_LID = 4, FLAG_GHOST = 8 };
+
+template <typename T>
+struct StepParams {
+	T *dd;
+	const int *flags;
+	T *velocity;
+	T *density;
+	long long n;             /* cells */
+	int sx, sy, sz;
+	long long sxy;
+	T inv_tau, tau, smag_k;
+	T gx, gy, gz, u_lid;
+	/* iteration box (cells): x0/nx multiples of VEC */
+	int x0, nx, y0, ny, z0, nz;
+	int wg;                  /* >0: emulate lbm_beta.cl:221-234 work-group x-shift */
+	int store_v, store_r;    /* write velocity / density arrays (only read when STORE) */
+};
+
+/* ---------------------------------------------------------------- vector access */
+template <typename T, int VEC> struct VecIO;
+
+template <> struct VecIO<float, 4> {
+	static __device__ __forceinline__ void load(const float *p, float (&v)[4]) {
+		float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+	}
+	static __device__ __forceinline__ void store(float *p, const float (&v)[4]) {
+		*reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+	}
+	/* p is 4 B past / before a 16 B boundary: 32 + 64 + 32 bit pieces */
+	static __device__ __forceinline__ void load_shifted(const float *p, float (&v)[4]) {
+		v[0] = p[0];
+		float2 t = *reinterpret_cast<const float2 *>(p + 1); v[1] = t.x; v[2] = t.y;
+		v[3] = p[3];
+	}
+	static __device__ __forceinline__ void store_shifted(float *p, const float (&v)[4]) {
+		p[0] = v[0];
+		*reinterpret_cast<float2 *>(p + 1) = make_float2(v[1], v[2]);
+		p[3] = v[3];
+	}
+};
+template <> struct VecIO<float, 2> {
+	static __device__ __forceinline__ void load(const float *p, float (&v)[2]) {
+		float2 t = *reinterpret_cast<const float2 *>(p); v[0] = t.x; v[1] = t.y;
+	}
+	static __device__ __forceinline__ void store(float *p, const float (&v)[2]) {
+		*reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+	}
+	static __device__ __forceinline__ void load_shifted(const float *p, float (&v)[2]) { v[0] = p[0]; v[1] = p[1]; }
+	static __device__ __forceinline__ void store_shifted(float *p, const float (&v)[2]) { p[0] = v[0]; p[1] = v[1]; }
+};
+template <> struct VecIO<double, 2> {
+	static __device__ __forceinline__ void load(const double *p, double (&v)[2]) {
+		double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y;
+	}
+	static __device__ __forceinline__ void store(double *p, const double (&v)[2]) {
+		*reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+	}
+	static __device__ __forceinline__ void load_shifted(const double *p, double (&v)[2]) { v[0] = p[0]; v[1] = p[1]; }
+	static __device__ __forceinline__ void store_shifted(double *p, const double (&v)[2]) { p[0] = v[0]; p[1] = v[1]; }
+};
+template <typename T> struct VecIO<T, 1> {
+	static __device__ __forceinline__ void load(const T *p, T (&v)[1]) { v[0] = p[0]; }
+	static __device__ __forceinline__ void store(T *p, const T (&v)[1]) { p[0] = v[0]; }
+	static __device__ __forceinline__ void load_shifted(const T *p, T (&v)[1]) { v[0] = p[0]; }
+	static __device__ __forceinline__ void store_shifted(T *p, const T (&v)[1]) { p[0] = v[0]; }
+};
+
+template <int VEC> struct FlagIO;
+template <> struct FlagIO<4> {
+	static __device__ __forceinline__ void load(const int *p, int (&v)[4]) {
+		int4 t = *reinterpret_cast<const int4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+	}
+};
+template <> struct FlagIO<2> {
+	static __device__ __forceinline__ void load(const int *p, int (&v)[2]) {
+		int2 t = *reinterpret_cast<const int2 *>(p); v[0] = t.x; v[1] = t.y;
+	}
+};
+template <> struct FlagIO<1> {
+	static __device__ __forceinline__ void load(const int *p, int (&v)[1]) { v[0] = p[0]; }
+};
+
+/* ---------------------------------------------------------------- equilibrium
+ * lbm_header.h:68-94; constants are float quotients cast to T, as in the reference. */
+template <typename T> struct Eq {
+	static __device__ __forceinline__ T w18() { return (T)(1.0f / 18.0f); }
+	static __device__ __forceinline__ T w36() { return (T)(1.0f / 36.0f); }
+	static __device__ __forceinline__ T w3()  { return (T)(1.0f / 3.0f); }
+	static __device__ __forceinline__ T a0(T v, T v2, T p) { return w18() * ((p + (T)(3.0f) * v) + (T)(9.0f / 2.0f) * v2); }
+	static __device__ __forceinline__ T a1(T v, T v2, T p) { return w18() * ((p + (T)(-3.0f) * v) + (T)(9.0f / 2.0f) * v2); }
+	static __device__ __forceinline__ T d4(T v, T v2, T p) { return w36() * ((p + (T)(3.0f) * v) + (T)(9.0f / 2.0f) * v2); }
+	static __device__ __forceinline__ T d5(T v, T v2, T p) { return w36() * ((p + (T)(-3.0f) * v) + (T)(9.0f / 2.0f) * v2); }
+	static __device__ __forceinline__ T c18(T p) { return w3() * p; }
+};
+
+__device__ __forceinline__ float  lbm_sqrt(float x)  { return sqrtf(x); }
+__device__ __forceinline__ double lbm_sqrt(double x) { return sqrt(x); }
+
+/* all 19 equilibria for (p = rho - 1.5 u^2, u) */
+template <typename T>
+__device__ __forceinline__ void equilibria(T (&eq)[19], T vx, T vy, T vz, T p)
+{
+	T v2, vv;
+	v2 = vx * vx; eq[0] = Eq<T>::a0(vx, v2, p); eq[1] = Eq<T>::a1(vx, v2, p);
+	v2 = vy * vy; eq[2] = Eq<T>::a0(vy, v2, p); eq[3] = Eq<T>::a1(vy, v2, p);
+	vv = vx + vy; v2 = vv * vv; eq[4] = Eq<T>::d4(vv, v2, p); eq[5] = Eq<T>::d5(vv, v2, p);
+	vv = vx - vy; v2 = vv * vv; eq[6] = Eq<T>::d4(vv, v2, p); eq[7] = Eq<T>::d5(vv, v2, p);
+	vv = vx + vz; v2 = vv * vv; eq[8] = Eq<T>::d4(vv, v2, p); eq[9] = Eq<T>::d5(vv, v2, p);
+	vv = vx - vz; v2 = vv * vv; eq[10] = Eq<T>::d4(vv, v2, p); eq[11] = Eq<T>::d5(vv, v2, p);
+	vv = vy + vz; v2 = vv * vv; eq[12] = Eq<T>::d4(vv, v2, p); eq[13] = Eq<T>::d5(vv, v2, p);
+	vv = vy - vz; v2 = vv * vv; eq[14] = Eq<T>::d4(vv, v2, p); eq[15] = Eq<T>::d5(vv, v2, p);
+	v2 = vz * vz; eq[16] = Eq<T>::a0(vz, v2, p); eq[17] = Eq<T>::a1(vz, v2, p);
+	eq[18] = Eq<T>::c18(p);
+}
+
+/* Smagorinsky closure: specification = oracle/lbm_oracle_impl.h smag_inv_tau (no reference
+ * counterpart).  Returns 1/tau_eff. */
+template <typename T>
+__device__ __forceinline__ T smagorinsky_inv_tau(const T (&d)[19], const T (&eq)[19], T rho, T tau, T smag_k)
+{
+	T q[19];
+#pragma unroll
+	for (int i = 0; i < 19; i++) q[i] = d[i] - eq[i];
+	T pxx = q[0]; pxx += q[1]; pxx += q[4]; pxx += q[5]; pxx += q[6]; pxx += q[7];
+	pxx += q[8]; pxx += q[9]; pxx += q[10]; pxx += q[11];
+	T pyy = q[2]; pyy += q[3]; pyy += q[4]; pyy += q[5]; pyy += q[6]; pyy += q[7];
+	pyy += q[12]; pyy += q[13]; pyy += q[14]; pyy += q[15];
+	T pzz = q[8]; pzz += q[9]; pzz += q[10]; pzz += q[11]; pzz += q[12]; pzz += q[13];
+	pzz += q[14]; pzz += q[15]; pzz += q[16]; pzz += q[17];
+	T pxy = q[4]; pxy += q[5]; pxy -= q[6]; pxy -= q[7];
+	T pxz = q[8]; pxz += q[9]; pxz -= q[10]; pxz -= q[11];
+	T pyz = q[12]; pyz += q[13]; pyz -= q[14]; pyz -= q[15];
+	T diag = pxx * pxx; diag += pyy * pyy; diag += pzz * pzz;
+	T off = pxy * pxy; off += pxz * pxz; off += pyz * pyz;
+	T pi_norm = lbm_sqrt(diag + (T)2.0f * off);
+	T t = tau * tau + (smag_k * pi_norm) / rho;
+	T tau_eff = (T)0.5f * (tau + lbm_sqrt(t));
+	return (T)1.0f / tau_eff;
+}
+
+/* moments in slot order: lbm_alpha.cl:61-156 and lbm_beta.cl:53-164 */
+template <typename T>
+__device__ __forceinline__ void moments_linear(const T (&d)[19], T &rho, T &vx, T &vy, T &vz)
+{
+	rho = d[0]; vx = d[0];
+	rho += d[1]; vx -= d[1];
+	rho += d[2]; vy = d[2];
+	rho += d[3]; vy -= d[3];
+	rho += d[4]; vx += d[4]; vy += d[4];
+	rho += d[5]; vx -= d[5]; vy -= d[5];
+	rho += d[6]; vx += d[6]; vy -= d[6];
+	rho += d[7]; vx -= d[7]; vy += d[7];
+	rho += d[8]; vx += d[8]; vz = d[8];
+	rho += d[9]; vx -= d[9]; vz -= d[9];
+	rho += d[10]; vx += d[10]; vz -= d[10];
+	rho += d[11]; vx -= d[11]; vz += d[11];
+	rho += d[12]; vy += d[12]; vz += d[12];
+	rho += d[13]; vy -= d[13]; vz -= d[13];
+	rho += d[14]; vy += d[14]; vz -= d[14];
+	rho += d[15]; vy -= d[15]; vz += d[15];
+	rho += d[16]; vz += d[16];
+	rho += d[17]; vz -= d[17];
+	rho += d[18];
+}
+
+/* moments in the order of the shipped shared-memory beta path: lbm_beta.cl:268-483 */
+template <typename T>
+__device__ __forceinline__ void moments_shipped(const T (&d)[19], T &rho, T &vx, T &vy, T &vz)
+{
+	rho = d[3]; vy = -d[3];
+	rho += d[2]; vy += d[2];
+	rho += d[0]; vx = d[0];
+	rho += d[1]; vx -= d[1];
+	rho += d[4]; vx += d[4]; vy += d[4];
+	rho += d[5]; vx -= d[5]; vy -= d[5];
+	rho += d[6]; vx += d[6]; vy -= d[6];
+	rho += d[7]; vx -= d[7]; vy += d[7];
+	rho += d[8]; vx += d[8]; vz = d[8];
+	rho += d[9]; vx -= d[9]; vz -= d[9];
+	rho += d[10]; vx += d[10]; vz -= d[10];
+	rho += d[11]; vx -= d[11]; vz += d[11];
+	rho += d[13]; vy -= d[13]; vz -= d[13];
+	rho += d[12]; vy += d[12]; vz += d[12];
+	rho += d[15]; vy -= d[15]; vz += d[15];
+	rho += d[14]; vy += d[14]; vz -= d[14];
+	rho += d[17]; vz -= d[17];
+	rho += d[16]; vz += d[16];
+	rho += d[18];
+}
+
+template <typename T>
+__device__ __forceinline__ void swap_pairs(T (&d)[19])
+{
+#pragma unroll
+	for (int i = 0; i < 18; i += 2) { T t = d[i + 1]; d[i + 1] = d[i]; d[i] = t; }
+}
+
+/* ---------------------------------------------------------------- alpha cell update
+ * lbm_alpha.cl:177-497.  On return d[i] holds the value the reference stores for
+ * direction i (it lands in slot i^1), `rho` the value it stores as density
+ * (`#define tmp rho`, :173).  Returns false when the reference writes nothing (obstacle,
+ * ghost, unknown flag): the caller then leaves the cell's slots untouched. */
+template <typename T, bool SMAG>
+__device__ __forceinline__ bool alpha_cell(T (&d)[19], int flag, const StepParams<T> &P,
+		T &rho, T &vx, T &vy, T &vz)
+{
+	moments_linear(d, rho, vx, vy, vz);
+	if (flag == FLAG_FLUID) {
+		const T vel2 = vx * vx + vy * vy + vz * vz;
+		const T p = rho - (T)(3.0f / 2.0f) * vel2;
+		T w = P.inv_tau;
+		if (SMAG) {
+			T eq[19];
+			equilibria(eq, vx, vy, vz, p);
+			w = smagorinsky_inv_tau(d, eq, rho, P.tau, P.smag_k);
+		}
+		T v2, vv;
+		rho = P.gx * (T)(1.0f / 18.0f) * rho;
+		v2 = vx * vx;
+		d[1] += w * (Eq<T>::a1(vx, v2, p) - d[1]); d[1] -= rho;
+		d[0] += w * (Eq<T>::a0(vx, v2, p) - d[0]); d[0] += rho;
+		rho = P.gy * (T)(-1.0f / 18.0f) * rho;
+		v2 = vy * vy;
+		d[3] += w * (Eq<T>::a1(vy, v2, p) - d[3]); d[3] -= rho;
+		d[2] += w * (Eq<T>::a0(vy, v2, p) - d[2]); d[2] += rho;
+		vv = vx + vy; v2 = vv * vv;
+		rho = (P.gx - P.gy) * (T)(1.0f / 36.0f) * rho;
+		d[5] += w * (Eq<T>::d5(vv, v2, p) - d[5]); d[5] -= rho;
+		d[4] += w * (Eq<T>::d4(vv, v2, p) - d[4]); d[4] += rho;
+		vv = vx - vy; v2 = vv * vv;
+		rho = (P.gx + P.gy) * (T)(1.0f / 36.0f) * rho;
+		d[7] += w * (Eq<T>::d5(vv, v2, p) - d[7]); d[7] -= rho;
+		d[6] += w * (Eq<T>::d4(vv, v2, p) - d[6]); d[6] += rho;
+		vv = vx + vz; v2 = vv * vv;
+		rho = (P.gx + P.gz) * (T)(1.0f / 36.0f) * rho;
+		d[9] += w * (Eq<T>::d5(vv, v2, p) - d[9]); d[9] -= rho;
+		d[8] += w * (Eq<T>::d4(vv, v2, p) - d[8]); d[8] += rho;
+		rho = (P.gx - P.gz) * (T)(1.0f / 36.0f) * rho;
+		vv = vx - vz; v2 = vv * vv;
+		d[11] += w * (Eq<T>::d5(vv, v2, p) - d[11]); d[11] -= rho;
+		d[10] += w * (Eq<T>::d4(vv, v2, p) - d[10]); d[10] += rho;
+		vv = vy + vz; v2 = vv * vv;
+		rho = (P.gz - P.gy) * (T)(1.0f / 36.0f) * rho;
+		d[13] += w * (Eq<T>::d5(vv, v2, p) - d[13]); d[13] -= rho;
+		d[12] += w * (Eq<T>::d4(vv, v2, p) - d[12]); d[12] += rho;
+		vv = vy - vz; v2 = vv * vv;
+		rho = (P.gz + P.gy) * (T)(-1.0f / 36.0f) * rho;
+		d[15] += w * (Eq<T>::d5(vv, v2, p) - d[15]); d[15] -= rho;
+		d[14] += w * (Eq<T>::d4(vv, v2, p) - d[14]); d[14] += rho;
+		v2 = vz * vz;
+		rho = P.gz * (T)(1.0f / 18.0f) * rho;
+		d[17] += w * (Eq<T>::a1(vz, v2, p) - d[17]); d[17] -= rho;
+		d[16] += w * (Eq<T>::a0(vz, v2, p) - d[16]); d[16] += rho;
+		d[18] += w * (Eq<T>::c18(p) - d[18]);
+		return true;
+	}
+	if (flag == FLAG_LID) {
+		vx = P.u_lid; vy = 0; vz = 0;
+		rho = 1.0f;
+		const T vel2 = vx * vx + vy * vy + vz * vz;
+		const T p = rho - (T)(3.0f / 2.0f) * vel2;
+		T v2, vv;
+		v2 = vx * vx;
+		rho = P.gx * (T)(1.0f / 18.0f) * rho;
+		d[1] = Eq<T>::a1(vx, v2, p); d[1] -= rho;
+		d[0] = Eq<T>::a0(vx, v2, p); d[0] += rho;
+		v2 = vy * vy;
+		rho = P.gy * (T)(-1.0f / 18.0f) * rho;
+		d[3] = Eq<T>::a1(vy, v2, p); d[3] -= rho;
+		d[2] = Eq<T>::a0(vy, v2, p); d[2] += rho;
+		vv = vx + vy; v2 = vv * vv;
+		rho = (P.gx - P.gy) * (T)(1.0f / 36.0f) * rho;
+		d[5] = Eq<T>::d5(vv, v2, p); d[5] -= rho;
+		d[4] = Eq<T>::d4(vv, v2, p); d[4] += rho;
+		vv = vx - vy; v2 = vv * vv;
+		rho = (P.gx + P.gy) * (T)(1.0f / 36.0f) * rho;
+		d[7] = Eq<T>::d5(vv, v2, p); d[7] -= rho;
+		d[6] = Eq<T>::d4(vv, v2, p); d[6] += rho;
+		vv = vx + vz; v2 = vv * vv;
+		rho = (P.gx + P.gz) * (T)(1.0f / 36.0f) * rho;
+		d[9] = Eq<T>::d5(vv, v2, p); d[9] -= rho;
+		d[8] = Eq<T>::d4(vv, v2, p); d[8] += rho;
+		vv = vx - vz; v2 = vv * vv;
+		rho = (P.gx - P.gz) * (T)(1.0f / 36.0f) * rho;
+		d[11] = Eq<T>::d5(vv, v2, p); d[11] -= rho;
+		d[10] = Eq<T>::d4(vv, v2, p); d[10] += rho;
+		vv = vy + vz; v2 = vv * vv;
+		rho = (P.gz - P.gy) * (T)(1.0f / 36.0f) * rho;
+		d[13] = Eq<T>::d5(vv, v2, p); d[13] -= rho;
+		d[12] = Eq<T>::d4(vv, v2, p); d[12] += rho;
+		vv = vy - vz; v2 = vv * vv;
+		rho = (P.gz + P.gy) * (T)(-1.0f / 36.0f) * rho;
+		d[15] = Eq<T>::d5(vv, v2, p); d[15] -= rho;
+		d[14] = Eq<T>::d4(vv, v2, p); d[14] += rho;
+		v2 = vz * vz;
+		rho = P.gz * (T)(1.0f / 18.0f) * rho;
+		d[17] = Eq<T>::a1(vz, v2, p); d[17] -= rho;
+		d[16] = Eq<T>::a0(vz, v2, p); d[16] += rho;
+		d[18] = Eq<T>::c18(p);
+		return true;
+	}
+	if (flag == FLAG_OBSTACLE) { vx = 0.0f; vy = 0.0f; vz = 0.0f; }
+	return false;
+}
+
+/* ---------------------------------------------------------------- beta cell update
+ * lbm_beta.cl:495-656 (+ moments).  d[i] in: pulled populations; out: values to push.
+ * `rho` out = what the reference stores as density (`#define dd_param rho`, :493). */
+template <typename T, bool SMAG, int ORDER>
+__device__ __forceinline__ void beta_cell(T (&d)[19], int flag, const StepParams<T> &P,
+		T &rho, T &vx, T &vy, T &vz)
+{
+	if (ORDER == 0) moments_shipped(d, rho, vx, vy, vz);
+	else moments_linear(d, rho, vx, vy, vz);
+	if (flag == FLAG_FLUID) {
+		const T vel2 = vx * vx + vy * vy + vz * vz;
+		T w = P.inv_tau;
+		const T rho_sum = rho;
+		rho = rho - (T)(3.0f / 2.0f) * vel2;
+		if (SMAG) {
+			T eq[19];
+			equilibria(eq, vx, vy, vz, rho);
+			w = smagorinsky_inv_tau(d, eq, rho_sum, P.tau, P.smag_k);
+		}
+		T v2, vv;
+		v2 = vx * vx;
+		d[0] += w * (Eq<T>::a0(vx, v2, rho) - d[0]);
+		d[1] += w * (Eq<T>::a1(vx, v2, rho) - d[1]);
+		v2 = vy * vy;
+		d[2] += w * (Eq<T>::a0(vy, v2, rho) - d[2]);
+		d[3] += w * (Eq<T>::a1(vy, v2, rho) - d[3]);
+		vv = vx + vy; v2 = vv * vv;
+		d[4] += w * (Eq<T>::d4(vv, v2, rho) - d[4]);
+		d[5] += w * (Eq<T>::d5(vv, v2, rho) - d[5]);
+		vv = vx - vy; v2 = vv * vv;
+		d[6] += w * (Eq<T>::d4(vv, v2, rho) - d[6]);
+		d[7] += w * (Eq<T>::d5(vv, v2, rho) - d[7]);
+		vv = vx + vz; v2 = vv * vv;
+		d[8] += w * (Eq<T>::d4(vv, v2, rho) - d[8]);
+		d[9] += w * (Eq<T>::d5(vv, v2, rho) - d[9]);
+		vv = vx - vz; v2 = vv * vv;
+		d[10] += w * (Eq<T>::d4(vv, v2, rho) - d[10]);
+		d[11] += w * (Eq<T>::d5(vv, v2, rho) - d[11]);
+		vv = vy + vz; v2 = vv * vv;
+		d[12] += w * (Eq<T>::d4(vv, v2, rho) - d[12]);
+		d[13] += w * (Eq<T>::d5(vv, v2, rho) - d[13]);
+		vv = vy - vz; v2 = vv * vv;
+		d[14] += w * (Eq<T>::d4(vv, v2, rho) - d[14]);
+		d[15] += w * (Eq<T>::d5(vv, v2, rho) - d[15]);
+		v2 = vz * vz;
+		d[16] += w * (Eq<T>::a0(vz, v2, rho) - d[16]);
+		d[17] += w * (Eq<T>::a1(vz, v2, rho) - d[17]);
+		d[18] += w * (Eq<T>::c18(rho) - d[18]);
+	} else if (flag == FLAG_OBSTACLE) {
+		vx = 0.0f; vy = 0.0f; vz = 0.0f;
+		swap_pairs(d);
+	} else if (flag == FLAG_LID) {
+		vx = P.u_lid; vy = 0; vz = 0;
+		rho = 1.0f;
+		const T vel2 = vx * vx + vy * vy + vz * vz;
+		rho = rho - (T)(3.0f / 2.0f) * vel2;
+		equilibria(d, vx, vy, vz, rho);
+	}
+}
+
+/* thread -> first cell of its VEC-wide group inside the iteration box; false = out of box */
+template <typename T, int VEC>
+__device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
+{
+	const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+	if (t >= (long long)P.nx * P.ny) return false;
+	long long off;
+	if (P.nx == P.sx) off = (long long)P.y0 * P.sx + t;
+	else { const int iy = (int)(t / P.nx), ix = (int)(t - (long long)iy * P.nx); off = (long long)(P.y0 + iy) * P.sx + P.x0 + ix; }
+	gid = (long long)(P.z0 + blockIdx.y) * P.sxy + off;
+	return true;
+}
+
+/* ================================================================== ALPHA kernel */
+template <typename T, int VEC, bool SMAG, bool STORE>
+__global__ void lbm_alpha_kernel(const StepParams<T> P)
+{
+	long long gid;
+	if (!box_cell<T, VEC>(P, gid)) return;
+
+	int flag[VEC];
+	FlagIO<VEC>::load(P.flags + gid, flag);
+	bool any_write = false;
+#pragma unroll
+	for (int e = 0; e < VEC; e++) any_write |= (flag[e] == FLAG_FLUID) | (flag[e] == FLAG_LID);
+	bool all_ghost = true;
+#pragma unroll
+	for (int e = 0; e < VEC; e++) all_ghost &= (flag[e] == FLAG_GHOST);
+	if (all_ghost) return;                       /* lbm_alpha.cl:31-32 */
+	if (!any_write && !STORE) return;            /* obstacle cells write nothing (:305-343) */
+
+	T v[19][VEC];
+	T *base = P.dd + gid;
+#pragma unroll
+	for (int i = 0; i < 19; i++) VecIO<T, VEC>::load(base + (long long)i * P.n, v[i]);
+
+	T orho[VEC], ovx[VEC], ovy[VEC], ovz[VEC];
+#pragma unroll
+	for (int e = 0; e < VEC; e++) {
+		T d[19];
+#pragma unroll
+		for (int i = 0; i < 19; i++) d[i] = v[i][e];
+		const bool wrote = alpha_cell<T, SMAG>(d, flag[e], P, orho[e], ovx[e], ovy[e], ovz[e]);
+		if (!wrote) {
+			/* the reference leaves slot j = old d[j]; the store below writes d[j^1] to slot j */
+#pragma unroll
+			for (int i = 0; i < 19; i++) d[i] = v[i][e];
+			swap_pairs(d);
+		}
+#pragma unroll
+		for (int i = 0; i < 19; i++) v[i][e] = d[i];
+	}
+	if (any_write) {
+#pragma unroll
+		for (int i = 0; i < 18; i++) VecIO<T, VEC>::store(base + (long long)i * P.n, v[i ^ 1]);
+		VecIO<T, VEC>::store(base + 18LL * P.n, v[18]);
+	}
+	if (STORE) {
+#pragma unroll
+		for (int e = 0; e < VEC; e++) {
+			if (flag[e] == FLAG_GHOST) continue;
+			if (P.store_v) {
+				P.velocity[gid + e] = ovx[e];
+				P.velocity[P.n + gid + e] = ovy[e];
+				P.velocity[2 * P.n + gid + e] = ovz[e];
+			}
+			if (P.store_r) P.density[gid + e] = orho[e];
+		}
+	}
+}
+
+/* ================================================================== BETA kernel */
+template <typename T, int VEC, bool SMAG, bool STORE, int ORDER>
+__global__ void lbm_beta_kernel(const StepParams<T> P)
+{
+	long long gid;
+	if (!box_cell<T, VEC>(P, gid)) return;
+
+	const long long DY = P.sx, DZ = P.sxy;
+	/* uniform per block: does any cell of this block reach across the linear array ends,
+	 * or is the reference's work-group x-shift observable (wg % sx == 0)? */
+	long long blk_lo, blk_hi;
+	{
+		const long long t0 = (long long)blockIdx.x * blockDim.x * VEC;
+		long long t1 = t0 + (long long)blockDim.x * VEC - 1;
+		const long long tmax = (long long)P.nx * P.ny - 1;
+		if (t1 > tmax) t1 = tmax;
+		long long o0, o1;
+		if (P.nx == P.sx) { o0 = (long long)P.y0 * P.sx + t0; o1 = (long long)P.y0 * P.sx + t1; }
+		else { o0 = (long long)(P.y0 + t0 / P.nx) * P.sx; o1 = (long long)(P.y0 + t1 / P.nx) * P.sx + P.sx - 1; }
+		const long long zb = (long long)(P.z0 + blockIdx.y) * P.sxy;
+		blk_lo = zb + o0; blk_hi = zb + o1;
+	}
+	const long long reach = DZ + DY + 1;
+	const bool general = (P.wg > 0) || (blk_lo < reach) || (blk_hi + reach >= P.n);
+
+	int flag[VEC];
+	FlagIO<VEC>::load(P.flags + gid, flag);
+
+	if (general) {
+		/* scalar path with the reference's linear periodic wrap (wrap.h:112-127) */
+#pragma unroll 1
+		for (int e = 0; e < VEC; e++) {
+			const long long c = gid + e;
+			long long xm = c - 1, xp = c + 1;
+			if (P.wg > 0) {
+				const int lid = (int)(c % P.wg);
+				if (lid == 0) xm = c + P.wg - 1;
+				if (lid == P.wg - 1) xp = c - (P.wg - 1);
+			}
+			long long L[18];
+			L[0] = xp;            L[1] = xm;
+			L[2] = c + DY;        L[3] = c - DY;
+			L[4] = xp + DY;       L[5] = xm - DY;
+			L[6] = xp - DY;       L[7] = xm + DY;
+			L[8] = xp + DZ;       L[9] = xm - DZ;
+			L[10] = xp - DZ;      L[11] = xm + DZ;
+			L[12] = c + DY + DZ;  L[13] = c - DY - DZ;
+			L[14] = c + DY - DZ;  L[15] = c - DY + DZ;
+			L[16] = c + DZ;       L[17] = c - DZ;
+#pragma unroll
+			for (int i = 0; i < 18; i++) {
+				while (L[i] < 0) L[i] += P.n;
+				while (L[i] >= P.n) L[i] -= P.n;
+				L[i] += (long long)i * P.n;
+			}
+			T d[19];
+#pragma unroll
+			for (int i = 0; i < 18; i++) d[i ^ 1] = P.dd[L[i]];
+			d[18] = P.dd[18LL * P.n + c];
+			T rho, vx, vy, vz;
+			beta_cell<T, SMAG, ORDER>(d, flag[e], P, rho, vx, vy, vz);
+#pragma unroll
+			for (int i = 0; i < 18; i++) P.dd[L[i]] = d[i];
+			P.dd[18LL * P.n + c] = d[18];
+			if (STORE && flag[e] != FLAG_GHOST) {
+				if (P.store_v) { P.velocity[c] = vx; P.velocity[P.n + c] = vy; P.velocity[2 * P.n + c] = vz; }
+				if (P.store_r) P.density[c] = rho;
+			}
+		}
+		return;
+	}
+
+	/* fast path: location (slot j, cell c + e_j) is read as d[j^1] and written as d[j] */
+	T *base = P.dd + gid;
+	T *loc[18];
+	loc[0] = base + 1;            loc[1] = base - 1;
+	loc[2] = base + DY;           loc[3] = base - DY;
+	loc[4] = base + 1 + DY;       loc[5] = base - 1 - DY;
+	loc[6] = base + 1 - DY;       loc[7] = base - 1 + DY;
+	loc[8] = base + 1 + DZ;       loc[9] = base - 1 - DZ;
+	loc[10] = base + 1 - DZ;      loc[11] = base - 1 + DZ;
+	loc[12] = base + DY + DZ;     loc[13] = base - DY - DZ;
+	loc[14] = base + DY - DZ;     loc[15] = base - DY + DZ;
+	loc[16] = base + DZ;          loc[17] = base - DZ;
+#pragma unroll
+	for (int i = 0; i < 18; i++) loc[i] += (long long)i * P.n;
+
+	T v[19][VEC];
+#pragma unroll
+	for (int i = 0; i < 18; i++) {
+		const bool shifted = (i < 2) || (i >= 4 && i < 12);     /* e_x != 0 */
+		if (shifted) VecIO<T, VEC>::load_shifted(loc[i], v[i ^ 1]);
+		else VecIO<T, VEC>::load(loc[i], v[i ^ 1]);
+	}
+	VecIO<T, VEC>::load(base + 18LL * P.n, v[18]);
+
+	T orho[VEC], ovx[VEC], ovy[VEC], ovz[VEC];
+#pragma unroll
+	for (int e = 0; e < VEC; e++) {
+		T d[19];
+#pragma unroll
+		for (int i = 0; i < 19; i++) d[i] = v[i][e];
+		beta_cell<T, SMAG, ORDER>(d, flag[e], P, orho[e], ovx[e], ovy[e], ovz[e]);
+#pragma unroll
+		for (int i = 0; i < 19; i++) v[i][e] = d[i];
+	}
+#pragma unroll
+	for (int i = 0; i < 18; i++) {
+		const bool shifted = (i < 2) || (i >= 4 && i < 12);
+		if (shifted) VecIO<T, VEC>::store_shifted(loc[i], v[i]);
+		else VecIO<T, VEC>::store(loc[i], v[i]);
+	}
+	VecIO<T, VEC>::store(base + 18LL * P.n, v[18]);
+
+	if (STORE) {
+#pragma unroll
+		for (int e = 0; e < VEC; e++) {
+			if (flag[e] == FLAG_GHOST) continue;
+			if (P.store_v) {
+				P.velocity[gid + e] = ovx[e];
+				P.velocity[P.n + gid + e] = ovy[e];
+				P.velocity[2 * P.n + gid + e] = ovz[e];
+			}
+			if (P.store_r) P.density[gid + e] = orho[e];
+		}
+	}
+}
+
+/* ================================================================== INIT kernel
+ * lbm_init.cl:32-237 */
+template <typename T>
+__global__ void lbm_init_kernel(T *dd, int *flags, T *velocity, T *density,
+		long long n, int sx, int sy, int sz, int b0, int b1, int b2, int b3, int b4, int b5,
+		int store_v, int store_r)
+{
+	const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= n) return;
+	const int x = (int)(gid % sx);
+	const int y = (int)((gid / sx) % sy);
+	const int z = (int)(gid / ((long long)sx * sy));
+	int flag = FLAG_FLUID;
+	if (x == 0) flag = b0;
+	else if (x == sx - 1) flag = b1;
+	else if (y == 0) flag = b2;
+	else if (y == sy - 1) flag = b3;
+	else if (z == 0) flag = b4;
+	else if (z == sz - 1) flag = b5;
+	T eq[19];
+	const T rho = 1.0f;
+	const T vx = 0, vy = 0, vz = 0;
+	const T p = rho - (T)(3.0f / 2.0f) * (vx * vx);       /* :133-134 */
+	equilibria(eq, vx, vy, vz, p);
+#pragma unroll
+	for (int i = 0; i < 19; i++) dd[(long long)i * n + gid] = eq[i];
+	flags[gid] = flag;
+	if (store_v) { velocity[gid] = vx; velocity[n + gid] = vy; velocity[2 * n + gid] = vz; }
+	if (store_r) density[gid] = rho;
+}
+
+/* ================================================================== rect copies
+ * copy_buffer_rect.cl:12-52 generalised: all components in ONE launch (the reference
+ * enqueues one launch per slot, src/CLbmSolver.hpp:704-711), 64-bit offsets (the
+ * reference's int offsets overflow at 512^3), optional per-component selection. */
+struct RectCopy {
+	long long src_comp_stride, dst_comp_stride;
+	int so[3], ss[3];        /* src origin, src array size  */
+	int dorg[3], ds[3];      /* dst origin, dst array size  */
+	int block[3];
+	int ncomp;               /* components to copy */
+	int src_comp[19];        /* component index on the src side */
+	int dst_comp[19];        /* component index on the dst side */
+};
+
+template <typename T>
+__global__ void rect_copy_kernel(const T *__restrict__ src, T *__restrict__ dst, const RectCopy R)
+{
+	const long long cells = (long long)R.block[0] * R.block[1] * R.block[2];
+	const long long total = cells * R.ncomp;
+	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+			t += (long long)gridDim.x * blockDim.x) {
+		const int c = (int)(t / cells);
+		long long r = t - (long long)c * cells;
+		const int k = (int)(r / ((long long)R.block[0] * R.block[1]));
+		r -= (long long)k * R.block[0] * R.block[1];
+		const int j = (int)(r / R.block[0]);
+		const int i = (int)(r - (long long)j * R.block[0]);
+		const long long s = (long long)R.src_comp[c] * R.src_comp_stride + (R.so[0] + i)
+				+ (long long)(R.so[1] + j) * R.ss[0] + (long long)(R.so[2] + k) * R.ss[0] * R.ss[1];
+		const long long d = (long long)R.dst_comp[c] * R.dst_comp_stride + (R.dorg[0] + i)
+				+ (long long)(R.dorg[1] + j) * R.ds[0] + (long long)(R.dorg[2] + k) * R.ds[0] * R.ds[1];
+		dst[d] = src[s];
+	}
+}
+
+/* ================================================================== checksum
+ * device-side variant of CLbmSolver::getVelocityChecksum: sum over FLUID cells of
+ * (ux+uy)+uz, accumulated in double with warp shuffles, one atomic per block. */
+template <typename T>
+__global__ void checksum_kernel(const T *__restrict__ velocity, const int *__restrict__ flags,
+		long long n, double *out)
+{
+	double acc = 0.0;
+	for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < n;
+			a += (long long)gridDim.x * blockDim.x)
+		if (flags[a] == FLAG_FLUID)
+			acc += (double)((velocity[a] + velocity[n + a]) + velocity[2 * n + a]);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+	__shared__ double warp_sums[32];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	if (lane == 0) warp_sums[wid] = acc;
+	__syncthreads();
+	if (wid == 0) {
+		acc = (lane < (blockDim.x + 31) / 32) ? warp_sums[lane] : 0.0;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+		if (lane == 0) atomicAdd(out, acc);
+	}
+}
+
+} /* namespace lbm */
