@@ -1,0 +1,338 @@
+#!/usr/bin/env python3
+"""bench.py -- MLUPS of the D3Q19 alpha/beta time step on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one lattice-Boltzmann time step (one alpha or beta pass over every cell of the
+sub-domain, plus the halo exchange when N > 1).  Workload (BASELINE.json configs[1]):
+lid-driven cavity, 256^3 cells per GPU, D3Q19, fp32, Smagorinsky LES (C_s = 0.1), conf.xml
+physics; for N > 1 the domain is z-slab decomposed (1,1,N) with 256^3 cells per GPU
+(weak scaling), ghost layers inside the sub-domain size as in the reference.
+MLUPS = steps * prod(global domain size) / seconds / 1e6 (reference src/CController.hpp:451-452).
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own kernels on the
+host CPU cores (oracle/_ref, built from /root/reference by oracle/build_ref.py) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE = 256
+CS = 0.1
+BYTES_PER_LUP_F32 = 2 * 19 * 4 + 4      # 156 B fp32, 308 B fp64
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def scenario(n_gpus, size=SIZE):
+    from turbulent_lbm_multigpu_b200.configuration import CConfiguration
+    cfg = CConfiguration()
+    cfg.domain_size = (size, size, size * n_gpus)
+    cfg.subdomain_num = (1, 1, n_gpus)
+    # weak scaling keeps the cell length (hence tau, u_lid) constant: benchmark.py:72
+    cfg.domain_length = (0.1, 0.1, 0.1 * n_gpus)
+    cfg.smagorinsky_constant = CS
+    cfg.loops = 0
+    return cfg
+
+
+# ====================================================================== reference arm
+def cpu_reference(size, budget_s=12.0, threads=None):
+    """The reference's kernels (oracle/_ref) on the host cores: bounded sample of the workload."""
+    from oracle import ref
+    from turbulent_lbm_multigpu_b200.skeleton import compute_parameters
+    p = compute_parameters((size,) * 3, (0.1,) * 3, dtype=np.float32)
+    fast = ref.available(fast=True)
+    kind = "reference"
+    if not ref.available(fast=fast):
+        raise RuntimeError("oracle/_ref is not built")
+    lib = ref.load(fast=fast)
+    if threads:
+        lib.ref_set_threads(threads)
+    cores = lib.ref_get_max_threads()
+    s = ref.RefSolver((size,) * 3, [1] * 6, p.inv_tau, p.gravitation, p.u_lid, variant=ref.NOSHM, fast=fast)
+    rect = (size - 2, 1, size - 2)
+    s.setFlags(np.full(rect[0] * rect[2], 4, np.int32), (1, size - 2, 1), rect)
+    s.simulationStep(); s.simulationStep()          # warm-up (one beta, one alpha)
+    t0 = time.perf_counter()
+    s.simulationStep(); s.simulationStep()
+    per = (time.perf_counter() - t0) / 2
+    steps = max(2, int(budget_s / max(per, 1e-6)) // 2 * 2)
+    steps = min(steps, 200)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.simulationStep()
+    dt = time.perf_counter() - t0
+    mlups = size ** 3 * steps / dt / 1e6
+    sample = ("%d steps of the %d^3 fp32 cavity, reference kernels lbm_alpha.cl/lbm_beta.cl (BGK -- the "
+              "reference has no Smagorinsky; beta via its own USE_SHARED_MEMORY 0 path) compiled as C++ "
+              "(%s), OpenMP over work-items" % (steps, size, "-O3 -march=x86-64-v3" if fast else "-O2 strict"))
+    return dict(value=mlups, unit="MLUPS", cores=cores, kind=kind, sample=sample), dt / steps * 1e3, steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cb, ms, steps = cpu_reference(SIZE, budget_s=max(4.0, min(60.0, 0.15 * args.steps)))
+    line = {
+        "impl": "reference", "metric": "MLUPS", "value": cb["value"], "unit": "MLUPS", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 2, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n):
+    return {"workload": "lid-driven cavity %d^3 per GPU D3Q19 fp32 Smagorinsky C_s=%g (BASELINE configs[1])" % (SIZE, CS),
+            "global_domain": [SIZE, SIZE, SIZE * n], "subdomain_num": [1, 1, n],
+            "parallelism": "z-slab domain decomposition, 1 process per GPU" if n > 1 else "single GPU",
+            "l2": "working set 1.34 GB per GPU >> 126 MB L2 (no flush needed)"}
+
+
+# ====================================================================== GPU arm
+def run_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n = args.gpus
+    if world != n:
+        if world == 1 and n > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (n, n))
+        n = world
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from turbulent_lbm_multigpu_b200.comm_backends import TorchDistributedBackend
+    from turbulent_lbm_multigpu_b200.controller import CManager
+    from turbulent_lbm_multigpu_b200.domain import CDomain
+
+    cfg = scenario(n)
+    domain = CDomain(-1, cfg.domain_size, (0, 0, 0), cfg.domain_length)
+    backend = TorchDistributedBackend() if world > 1 else None
+    mgr = CManager(domain, cfg.subdomain_num, backend=backend, device=local, config=cfg,
+                   sync_mode=args.sync if world > 1 else "host", dtype=np.float32,
+                   store_velocity=False, store_density=False)
+    mgr.initSimulation(rank)
+    ctrl = mgr.getController()
+    s = ctrl.getSolver()
+    cells_global = int(np.prod(cfg.domain_size))
+    cells_local = int(np.prod(mgr.getSubdomainSize()))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W, K = max(3, args.warmup), args.steps
+    for _ in range(W):
+        ctrl.computeNextStep()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = s.launchCount()
+    s.timerStart()
+    for _ in range(K):
+        ctrl.computeNextStep()
+    ms = s.timerStop()                     # CUDA events on the launching (compute) stream
+    barrier()
+    launches = s.launchCount() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = cells_global * K / (ms * 1e-3) / 1e6
+
+    # ---- per-kernel timing (alpha / beta alone), single GPU only: explains the roofline
+    kern = {}
+    if world == 1:
+        for name, fn in (("lbm_alpha_kernel", s.simulationStepAlpha), ("lbm_beta_kernel", s.simulationStepBeta)):
+            for _ in range(3):
+                fn()
+            s.wait()
+            s.timerStart()
+            reps = 20
+            for _ in range(reps):
+                fn()
+            kms = s.timerStop() / reps
+            kern[name] = {"ms": kms, "GBs": BYTES_PER_LUP_F32 * cells_local / (kms * 1e-3) / 1e9}
+
+    # ---- end to end through the public host API with HOST buffers every step
+    e2e = None
+    if world == 1:
+        S = SIZE
+        rect = (S - 2, 1, S - 2)
+        lid = torch.full((rect[0] * rect[2],), 4, dtype=torch.int32).pin_memory()
+        probe = torch.empty(19 * S, dtype=torch.float32).pin_memory()
+        lid_np, probe_np = lid.numpy(), probe.numpy()
+        po, ps = (S // 2, 0, S // 2), (1, S, 1)
+        for _ in range(3):
+            s.setFlags(lid_np, (1, S - 2, 1), rect); s.simulationStep(); s.storeDensityDistribution(probe_np, po, ps)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            s.setFlags(lid_np, (1, S - 2, 1), rect)             # H2D: boundary input of the step
+            s.simulationStep()
+            s.storeDensityDistribution(probe_np, po, ps)         # D2H: populations on the centre line
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": cells_global * K / dt / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": int(lid_np.nbytes), "d2h_bytes_per_step": int(probe_np.nbytes),
+               "api": "CLbmSolver.setFlags + simulationStep + storeDensityDistribution (pinned host buffers)"}
+    else:
+        # multi-GPU: every rank uploads its lid rect and reads back its probe line each step
+        S = SIZE
+        rect = (S - 2, 1, S - 2)
+        lid_np = torch.full((rect[0] * rect[2],), 4, dtype=torch.int32).pin_memory().numpy()
+        probe_np = torch.empty(19 * S, dtype=torch.float32).pin_memory().numpy()
+        po, ps = (S // 2, 0, S // 2), (1, S, 1)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            s.setFlags(lid_np, (1, S - 2, 1), rect)
+            ctrl.computeNextStep()
+            s.storeDensityDistribution(probe_np, po, ps)
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": cells_global * K / float(t.item()) / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": int(lid_np.nbytes) * n, "d2h_bytes_per_step": int(probe_np.nbytes) * n,
+               "api": "CLbmSolver.setFlags + CController.computeNextStep + storeDensityDistribution"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = BYTES_PER_LUP_F32 * cells_local / (ms * 1e-3 / 1.0) / 1e9   # per GPU, per step
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": n, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(n),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": BYTES_PER_LUP_F32 * cells_local * K / (ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s",
+                         "frac": BYTES_PER_LUP_F32 * cells_local * K / (ms * 1e-3) / 1e9 / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES_PER_LUP_F32 * cells_local,
+                         "kernels": kern,
+                         "note": "step kernels lbm_alpha_kernel/lbm_beta_kernel alternate; 156 B per "
+                                 "lattice-site update x cells per launch / CUDA-event time"},
+            "sync_mode": args.sync if world > 1 else None,
+            "kernel_config": s.config(),
+        }
+        del achieved
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb, _, _ = cpu_reference(SIZE, budget_s=args.cpu_budget)
+                line["cpu_baseline"] = cb
+            except Exception as e:    # the checker being absent must not hide the GPU result
+                line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": "unavailable: %s" % e}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sync", default="overlap", choices=["host", "device", "overlap"])
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,79 @@
+"""Multi-sub-domain parity on the GPU: the reference's own validate criterion
+(src/main.cpp:309-408) -- an n-way decomposed run must equal the single domain of size
+D - 2(n-1) bit for bit on the interior blocks -- plus equality with the oracle's decomposed
+run on every population of every sub-domain (ghost layers included)."""
+import numpy as np
+import pytest
+
+from helpers import bits_equal
+from oracle import multi as omulti
+from turbulent_lbm_multigpu_b200 import capi
+from turbulent_lbm_multigpu_b200.configuration import CConfiguration
+from turbulent_lbm_multigpu_b200.controller import (InProcessSimulation, validation_domain_size,
+                                                    validation_sub_origin)
+from turbulent_lbm_multigpu_b200.domain import CDomain
+from turbulent_lbm_multigpu_b200.solver import CLbmSolver
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg():
+    c = CConfiguration()
+    c.debug_mode = True      # STORE_VELOCITY / STORE_DENSITY on, like a DEBUG build of the reference
+    return c
+
+
+@pytest.mark.parametrize("D,nums,steps", [
+    ((32, 16, 16), (2, 1, 1), 40),
+    ((36, 16, 16), (3, 1, 1), 41),
+    ((16, 16, 24), (1, 1, 2), 60),
+    ((16, 24, 16), (1, 2, 1), 61),
+    ((24, 24, 12), (2, 2, 1), 60),
+    ((24, 24, 24), (2, 2, 2), 81),
+    ((64, 32, 48), (2, 1, 3), 30),
+])
+@pytest.mark.parametrize("slots", [capi.LBM_HALO_SLOTS_MINIMAL, capi.LBM_HALO_SLOTS_REFERENCE])
+def test_decomposed_equals_single_domain(D, nums, steps, slots):
+    L = (0.1, 0.1, 0.1)
+    sim = InProcessSimulation(CDomain(-1, D, (0, 0, 0), L), nums, slots=slots, config=_cfg(),
+                              dtype=np.float32, beta_order=capi.LBM_BETA_ORDER_LINEAR)
+    sim.run(steps)
+    p = sim.controllers[0].getSolver().params
+    V = validation_domain_size(D, nums)
+    single = CLbmSolver(0, 0, [[1, 1]] * 3, CDomain(0, V, (0, 0, 0), L), dtype=np.float32, store_velocity=True,
+                        store_density=True, beta_order=capi.LBM_BETA_ORDER_LINEAR, params=p)
+    rect = (V[0] - 2, 1, V[2] - 2)
+    single.setFlags(np.full(rect[0] * rect[2], 4, np.int32), (1, V[1] - 2, 1), rect)
+    single.simulationSteps(steps)
+    inner = tuple(s - 2 for s in sim.sub_size)
+    for r, ctrl in enumerate(sim.controllers):
+        o = validation_sub_origin(r, nums, inner)
+        s = ctrl.getSolver()
+        assert bits_equal(s.storeVelocity(origin=(1, 1, 1), size=inner), single.storeVelocity(origin=o, size=inner)), (r, "velocity")
+        assert bits_equal(s.storeFlags(origin=(1, 1, 1), size=inner), single.storeFlags(origin=o, size=inner)), (r, "flags")
+        fl = s.storeFlags(origin=(1, 1, 1), size=inner)
+        m = np.isin(fl, (2, 4))
+        a, b = s.storeDensity(origin=(1, 1, 1), size=inner), single.storeDensity(origin=o, size=inner)
+        assert bits_equal(a[m], b[m]), (r, "density")
+
+    # and against the oracle's decomposed run: every population of every rank
+    make, po = omulti.make_oracle_factory(D, nums, L, dtype=np.float32, variant=1)
+    md = omulti.MultiDomain(D, nums, make, slots="minimal" if slots == capi.LBM_HALO_SLOTS_MINIMAL else "reference")
+    md.run(steps)
+    for r, ctrl in enumerate(sim.controllers):
+        assert bits_equal(ctrl.getSolver().storeDensityDistribution(), md.ranks[r]["solver"].dd), (r, "dd vs oracle")
+
+
+def test_comm_tables_match_the_oracle_restatement():
+    from turbulent_lbm_multigpu_b200.controller import CManager
+    D, nums = (24, 36, 48), (2, 3, 4)
+    m = CManager.__new__(CManager)
+    m._domain = CDomain(-1, D, (0, 0, 0), (0.1,) * 3)
+    m._controller_kw = {}
+    m.setSubdomainNums(nums)
+    sub = omulti.decompose(D, nums)
+    for r in range(24):
+        rid, coords, BC, comms, origin = m.layout(r)
+        ocoords, obc, ocomms, oorigin = omulti.rank_layout(r, nums, sub)
+        assert coords == ocoords and BC == obc and origin == oorigin
+        assert [c.as_tuple() for c in comms] == [c.as_tuple() for c in ocomms]

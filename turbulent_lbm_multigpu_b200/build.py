@@ -37,17 +37,19 @@ def deps():
     return sources() + [os.path.join(CSRC, "lbm_kernels.cuh"), os.path.join(ROOT, "include", "lbm_b200.h")]
 
 
-def build(force=False, verbose=False, extra=()):
+def build(force=False, verbose=False, extra=(), out=None):
+    """extra/out: tuning variants (e.g. -DLBM_LB_BETA=__launch_bounds__(256,2)) under another name."""
     os.makedirs(LIBDIR, exist_ok=True)
-    if (not force and os.path.exists(LIB)
-            and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps())):
-        return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + sources()
+    lib = out or LIB
+    if (not force and os.path.exists(lib)
+            and os.path.getmtime(lib) >= max(os.path.getmtime(d) for d in deps())):
+        return lib
+    cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-o", lib] + sources()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "liblbm_b200.so")
+# LBM_B200_LIB: tuning hook to load an alternative build of the SAME CUDA library
+LIB_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(HERE, "lib", "liblbm_b200.so")
 
 LBM_OK = 0
 LBM_F32, LBM_F64 = 0, 1

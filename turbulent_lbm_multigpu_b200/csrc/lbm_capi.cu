@@ -90,15 +90,34 @@ template <typename T, int VEC, bool SMAG, bool STORE>
 void launch_alpha(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStream_t s)
 {
 	lbm_alpha_kernel<T, VEC, SMAG, STORE><<<grid, block, 0, s>>>(P);
+	h->launches++;
 }
 
 template <typename T, int VEC, bool SMAG, bool STORE>
 void launch_beta(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStream_t s)
 {
-	if (h->desc.beta_order == LBM_BETA_ORDER_SHIPPED)
-		lbm_beta_kernel<T, VEC, SMAG, STORE, 0><<<grid, block, 0, s>>>(P);
-	else
-		lbm_beta_kernel<T, VEC, SMAG, STORE, 1><<<grid, block, 0, s>>>(P);
+	const bool shipped = h->desc.beta_order == LBM_BETA_ORDER_SHIPPED;
+	if (P.wg == 0) {   /* with the work-group quirk live every block takes the general path */
+		if (shipped) lbm_beta_kernel<T, VEC, SMAG, STORE, 0><<<grid, block, 0, s>>>(P);
+		else lbm_beta_kernel<T, VEC, SMAG, STORE, 1><<<grid, block, 0, s>>>(P);
+		h->launches++;
+	}
+	/* general kernel: only z planes whose blocks can reach across the array ends
+	 * (|delta| <= sxy + sx + 1 -> planes 0,1 and sz-2,sz-1), or everything with the quirk */
+	const int zlo_end = P.wg > 0 ? P.sz : 2, zhi_begin = P.wg > 0 ? P.sz : P.sz - 2;
+	int ranges[2][2] = { { P.z0, (P.z0 + P.nz < zlo_end ? P.z0 + P.nz : zlo_end) },
+	                     { (P.z0 > zhi_begin ? P.z0 : zhi_begin), P.z0 + P.nz } };
+	if (ranges[1][0] < ranges[0][1]) ranges[1][0] = ranges[0][1];
+	for (int r = 0; r < 2; r++) {
+		const int z0 = ranges[r][0], z1 = ranges[r][1];
+		if (z1 <= z0) continue;
+		StepParams<T> Q = P;
+		Q.z0 = z0; Q.nz = z1 - z0;
+		dim3 g2(grid.x, (unsigned)Q.nz);
+		if (shipped) lbm_beta_general_kernel<T, VEC, SMAG, STORE, 0><<<g2, block, 0, s>>>(Q);
+		else lbm_beta_general_kernel<T, VEC, SMAG, STORE, 1><<<g2, block, 0, s>>>(Q);
+		h->launches++;
+	}
 }
 
 template <typename T, int VEC>
@@ -119,7 +138,6 @@ int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s)
 	} while (0)
 	if (alpha) LBM_DISPATCH(launch_alpha); else LBM_DISPATCH(launch_beta);
 #undef LBM_DISPATCH
-	h->launches++;
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
 }
@@ -344,7 +362,9 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	h->smag = d->smagorinsky_cs != 0.0;
 	h->u_lid = d->u_lid;
 	const int maxvec = d->dtype == LBM_F32 ? 4 : 2;
-	int vec = d->vector_width > 0 ? d->vector_width : maxvec;
+	/* default: 2 cells per thread (measured best on B200 for fp32: 96 registers -> 20 resident
+	 * warps per SM, profiles/r1_sweep_launch_config.md); 4 is available on request */
+	int vec = d->vector_width > 0 ? d->vector_width : 2;
 	if (vec > maxvec) vec = maxvec;
 	while (vec > 1 && (h->sx % vec) != 0) vec >>= 1;
 	if (vec != 1 && vec != 2 && vec != 4) vec = 1;

@@ -21,6 +21,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+/* launch bounds are a tuning knob (registers vs resident warps); see DESIGN.md */
+#if defined(LBM_LB_MAXT) && defined(LBM_LB_MINB)
+#define LBM_LB_ALPHA __launch_bounds__(LBM_LB_MAXT, LBM_LB_MINB)
+#define LBM_LB_BETA __launch_bounds__(LBM_LB_MAXT, LBM_LB_MINB)
+#else
+#define LBM_LB_ALPHA
+#define LBM_LB_BETA
+#endif
+
 namespace lbm {
 
 enum : int { FLAG_OBSTACLE = 1, FLAG_FLUID = 2, FLAG_LID = 4, FLAG_GHOST = 8 };
@@ -404,7 +413,7 @@ __device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
 
 /* ================================================================== ALPHA kernel */
 template <typename T, int VEC, bool SMAG, bool STORE>
-__global__ void lbm_alpha_kernel(const StepParams<T> P)
+__global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 {
 	long long gid;
 	if (!box_cell<T, VEC>(P, gid)) return;
@@ -460,79 +469,41 @@ __global__ void lbm_alpha_kernel(const StepParams<T> P)
 	}
 }
 
-/* ================================================================== BETA kernel */
+/* ================================================================== BETA kernels
+ * Two kernels share one thread->cell mapping and one block-uniform predicate:
+ *   lbm_beta_kernel          vectorised, wrap-free path; blocks that need wrapping exit;
+ *   lbm_beta_general_kernel  scalar path with the reference's linear periodic wrap
+ *                            (wrap.h:112-127) and work-group x-shift; only the blocks the
+ *                            fast kernel skipped do work (launched on the outer planes only).
+ * Keeping them apart keeps the wrap bookkeeping out of the hot kernel's register budget. */
+template <typename T, int VEC>
+__device__ __forceinline__ bool beta_block_is_general(const StepParams<T> &P)
+{
+	if (P.wg > 0) return true;
+	const long long t0 = (long long)blockIdx.x * blockDim.x * VEC;
+	long long t1 = t0 + (long long)blockDim.x * VEC - 1;
+	const long long tmax = (long long)P.nx * P.ny - 1;
+	if (t1 > tmax) t1 = tmax;
+	long long o0, o1;
+	if (P.nx == P.sx) { o0 = (long long)P.y0 * P.sx + t0; o1 = (long long)P.y0 * P.sx + t1; }
+	else { o0 = (long long)(P.y0 + t0 / P.nx) * P.sx; o1 = (long long)(P.y0 + t1 / P.nx) * P.sx + P.sx - 1; }
+	const long long zb = (long long)(P.z0 + blockIdx.y) * P.sxy;
+	const long long reach = P.sxy + P.sx + 1;
+	return (zb + o0 < reach) || (zb + o1 + reach >= P.n);
+}
+
 template <typename T, int VEC, bool SMAG, bool STORE, int ORDER>
-__global__ void lbm_beta_kernel(const StepParams<T> P)
+__global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 {
 	long long gid;
 	if (!box_cell<T, VEC>(P, gid)) return;
+	if (beta_block_is_general<T, VEC>(P)) return;
 
 	const long long DY = P.sx, DZ = P.sxy;
-	/* uniform per block: does any cell of this block reach across the linear array ends,
-	 * or is the reference's work-group x-shift observable (wg % sx == 0)? */
-	long long blk_lo, blk_hi;
-	{
-		const long long t0 = (long long)blockIdx.x * blockDim.x * VEC;
-		long long t1 = t0 + (long long)blockDim.x * VEC - 1;
-		const long long tmax = (long long)P.nx * P.ny - 1;
-		if (t1 > tmax) t1 = tmax;
-		long long o0, o1;
-		if (P.nx == P.sx) { o0 = (long long)P.y0 * P.sx + t0; o1 = (long long)P.y0 * P.sx + t1; }
-		else { o0 = (long long)(P.y0 + t0 / P.nx) * P.sx; o1 = (long long)(P.y0 + t1 / P.nx) * P.sx + P.sx - 1; }
-		const long long zb = (long long)(P.z0 + blockIdx.y) * P.sxy;
-		blk_lo = zb + o0; blk_hi = zb + o1;
-	}
-	const long long reach = DZ + DY + 1;
-	const bool general = (P.wg > 0) || (blk_lo < reach) || (blk_hi + reach >= P.n);
-
 	int flag[VEC];
 	FlagIO<VEC>::load(P.flags + gid, flag);
 
-	if (general) {
-		/* scalar path with the reference's linear periodic wrap (wrap.h:112-127) */
-#pragma unroll 1
-		for (int e = 0; e < VEC; e++) {
-			const long long c = gid + e;
-			long long xm = c - 1, xp = c + 1;
-			if (P.wg > 0) {
-				const int lid = (int)(c % P.wg);
-				if (lid == 0) xm = c + P.wg - 1;
-				if (lid == P.wg - 1) xp = c - (P.wg - 1);
-			}
-			long long L[18];
-			L[0] = xp;            L[1] = xm;
-			L[2] = c + DY;        L[3] = c - DY;
-			L[4] = xp + DY;       L[5] = xm - DY;
-			L[6] = xp - DY;       L[7] = xm + DY;
-			L[8] = xp + DZ;       L[9] = xm - DZ;
-			L[10] = xp - DZ;      L[11] = xm + DZ;
-			L[12] = c + DY + DZ;  L[13] = c - DY - DZ;
-			L[14] = c + DY - DZ;  L[15] = c - DY + DZ;
-			L[16] = c + DZ;       L[17] = c - DZ;
-#pragma unroll
-			for (int i = 0; i < 18; i++) {
-				while (L[i] < 0) L[i] += P.n;
-				while (L[i] >= P.n) L[i] -= P.n;
-				L[i] += (long long)i * P.n;
-			}
-			T d[19];
-#pragma unroll
-			for (int i = 0; i < 18; i++) d[i ^ 1] = P.dd[L[i]];
-			d[18] = P.dd[18LL * P.n + c];
-			T rho, vx, vy, vz;
-			beta_cell<T, SMAG, ORDER>(d, flag[e], P, rho, vx, vy, vz);
-#pragma unroll
-			for (int i = 0; i < 18; i++) P.dd[L[i]] = d[i];
-			P.dd[18LL * P.n + c] = d[18];
-			if (STORE && flag[e] != FLAG_GHOST) {
-				if (P.store_v) { P.velocity[c] = vx; P.velocity[P.n + c] = vy; P.velocity[2 * P.n + c] = vz; }
-				if (P.store_r) P.density[c] = rho;
-			}
-		}
-		return;
-	}
-
-	/* fast path: location (slot j, cell c + e_j) is read as d[j^1] and written as d[j] */
+	/* location (slot j, cell c + e_j) is read as d[j^1] and written as d[j] */
 	T *base = P.dd + gid;
 	T *loc[18];
 	loc[0] = base + 1;            loc[1] = base - 1;
@@ -584,6 +555,55 @@ __global__ void lbm_beta_kernel(const StepParams<T> P)
 				P.velocity[2 * P.n + gid + e] = ovz[e];
 			}
 			if (P.store_r) P.density[gid + e] = orho[e];
+		}
+	}
+}
+
+template <typename T, int VEC, bool SMAG, bool STORE, int ORDER>
+__global__ void lbm_beta_general_kernel(const StepParams<T> P)
+{
+	long long gid;
+	if (!box_cell<T, VEC>(P, gid)) return;
+	if (!beta_block_is_general<T, VEC>(P)) return;
+	const long long DY = P.sx, DZ = P.sxy;
+#pragma unroll 1
+	for (int e = 0; e < VEC; e++) {
+		const long long c = gid + e;
+		const int flag = P.flags[c];
+		long long xm = c - 1, xp = c + 1;
+		if (P.wg > 0) {
+			const int lid = (int)(c % P.wg);
+			if (lid == 0) xm = c + P.wg - 1;
+			if (lid == P.wg - 1) xp = c - (P.wg - 1);
+		}
+		long long L[18];
+		L[0] = xp;            L[1] = xm;
+		L[2] = c + DY;        L[3] = c - DY;
+		L[4] = xp + DY;       L[5] = xm - DY;
+		L[6] = xp - DY;       L[7] = xm + DY;
+		L[8] = xp + DZ;       L[9] = xm - DZ;
+		L[10] = xp - DZ;      L[11] = xm + DZ;
+		L[12] = c + DY + DZ;  L[13] = c - DY - DZ;
+		L[14] = c + DY - DZ;  L[15] = c - DY + DZ;
+		L[16] = c + DZ;       L[17] = c - DZ;
+#pragma unroll
+		for (int i = 0; i < 18; i++) {
+			while (L[i] < 0) L[i] += P.n;
+			while (L[i] >= P.n) L[i] -= P.n;
+			L[i] += (long long)i * P.n;
+		}
+		T d[19];
+#pragma unroll
+		for (int i = 0; i < 18; i++) d[i ^ 1] = P.dd[L[i]];
+		d[18] = P.dd[18LL * P.n + c];
+		T rho, vx, vy, vz;
+		beta_cell<T, SMAG, ORDER>(d, flag, P, rho, vx, vy, vz);
+#pragma unroll
+		for (int i = 0; i < 18; i++) P.dd[L[i]] = d[i];
+		P.dd[18LL * P.n + c] = d[18];
+		if (STORE && flag != FLAG_GHOST) {
+			if (P.store_v) { P.velocity[c] = vx; P.velocity[P.n + c] = vy; P.velocity[2 * P.n + c] = vz; }
+			if (P.store_r) P.density[c] = rho;
 		}
 	}
 }
