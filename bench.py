@@ -187,9 +187,13 @@ def run_gpu(args):
     cfg = scenario(n)
     domain = CDomain(-1, cfg.domain_size, (0, 0, 0), cfg.domain_length)
     backend = TorchDistributedBackend() if world > 1 else None
+    # the library launches on torch-owned streams so that NCCL (torch.distributed) and a
+    # CUDA-graph capture of the two-step cycle see the same stream order
+    compute_stream, comm_stream = torch.cuda.Stream(), torch.cuda.Stream()
     mgr = CManager(domain, cfg.subdomain_num, backend=backend, device=local, config=cfg,
                    sync_mode=args.sync if world > 1 else "host", dtype=np.float32,
-                   store_velocity=False, store_density=False)
+                   store_velocity=False, store_density=False,
+                   compute_stream=compute_stream.cuda_stream, comm_stream=comm_stream.cuda_stream)
     mgr.initSimulation(rank)
     ctrl = mgr.getController()
     s = ctrl.getSolver()
@@ -202,19 +206,45 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     W, K = max(3, args.warmup), args.steps
+    W += W & 1                              # whole beta/alpha cycles
+    K += K & 1
     for _ in range(W):
         ctrl.computeNextStep()
     barrier()
+    # launch-bound inner loop: capture the beta+alpha cycle (kernels, stream edges, NCCL
+    # send/recv) into one CUDA graph and replay it
+    graph, per_cycle = None, 0
+    if world > 1 and args.graph:
+        try:
+            l0 = s.launchCount()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=compute_stream, capture_error_mode="thread_local"):
+                ctrl.computeNextStep()
+                ctrl.computeNextStep()
+            per_cycle = s.launchCount() - l0
+            with torch.cuda.stream(compute_stream):
+                graph.replay()              # warm the instantiated graph
+            barrier()
+        except Exception as e:              # keep the eager path usable
+            if rank == 0:
+                print("cuda graph capture unavailable (%s): eager launches" % e, file=sys.stderr)
+            graph = None
+            barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = s.launchCount()
     s.timerStart()
-    for _ in range(K):
-        ctrl.computeNextStep()
+    if graph is not None:
+        with torch.cuda.stream(compute_stream):
+            for _ in range(K // 2):
+                graph.replay()
+    else:
+        for _ in range(K):
+            ctrl.computeNextStep()
     ms = s.timerStop()                     # CUDA events on the launching (compute) stream
     barrier()
-    launches = s.launchCount() - launches0
+    launches = (K // 2) * per_cycle if graph is not None else s.launchCount() - launches0
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -301,7 +331,7 @@ def run_gpu(args):
                          "kernels": kern,
                          "note": "step kernels lbm_alpha_kernel/lbm_beta_kernel alternate; 156 B per "
                                  "lattice-site update x cells per launch / CUDA-event time"},
-            "sync_mode": args.sync if world > 1 else None,
+            "sync_mode": args.sync if world > 1 else None, "cuda_graph": graph is not None,
             "kernel_config": s.config(),
         }
         del achieved
@@ -325,9 +355,11 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sync", default="overlap", choices=["host", "device", "overlap"])
+    ap.add_argument("--sync", default="p2p", choices=["host", "device", "overlap", "p2p"],
+                    help="halo transport for N > 1 (p2p: one-sided NVLink peer stores; overlap/device: NCCL)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="capture the 2-step cycle in a CUDA graph (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

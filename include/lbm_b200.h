@@ -155,6 +155,26 @@ int lbmHaloUnpack(lbm_t h, const int origin[3], const int size[3], uint32_t buf_
 int lbmHaloCopyPeer(lbm_t src, const int src_origin[3], lbm_t dst, const int dst_origin[3],
 		const int size[3], uint32_t slot_mask, void *stream);
 
+/* ---- one-sided halo exchange over NVLink peer memory (no NCCL, no host staging) --------
+ * A face = one CComm (src/CComm.hpp:8-79).  Each face owns a RECEIVE block in device memory
+ * ([flag words][alpha staging][beta staging]); the neighbour maps it (same process: directly;
+ * other process: CUDA IPC) and its push kernel packs the face and stores it straight into
+ * that block over NVLink, then raises the block's flag word; the owner's pull waits on the
+ * flag (device side) and unpacks.  Replaces syncAlpha/syncBeta (src/CController.hpp:265-383). */
+int lbmCommAddFace(lbm_t h, int dst_rank, const int send_origin[3], const int recv_origin[3],
+		const int size[3], const int dir[3], int slots, int *face_id);
+int lbmCommFaceCount(lbm_t h, int *count);
+int lbmCommGetIpcHandle(lbm_t h, int face_id, void *handle64);            /* 64-byte cudaIpcMemHandle_t */
+int lbmCommConnectIpc(lbm_t h, int face_id, const void *peer_handle64);   /* peer in another process */
+int lbmCommConnectLocal(lbm_t h, int face_id, lbm_t peer, int peer_face_id); /* peer in this process */
+int lbmCommBeginSync(lbm_t h, int sync_kind);           /* next sequence number of that sync kind */
+int lbmCommPush(lbm_t h, int sync_kind, int axis);      /* push my faces of one axis (comm stream) */
+int lbmCommPull(lbm_t h, int sync_kind, int axis);      /* wait + unpack my faces of one axis */
+int lbmCommSync(lbm_t h, int sync_kind);                /* begin; for axis x,y,z: push; pull */
+/* one overlapped time step: shell kernels -> (push/pull on the comm stream || interior kernel)
+ * -> join; == CController::computeNextStep (src/CController.hpp:385-391) */
+int lbmCommStep(lbm_t h);
+
 /* ---- overlap support: the step split into the shell next to ghost faces and the interior.
  *      ghost_faces: bit a*2+s set = face (axis a, side s) has a neighbour. --------------- */
 int lbmStepShell(lbm_t h, int ghost_faces);     /* launches on the compute stream */

@@ -76,6 +76,16 @@ SYMBOLS = {
     "lbmHaloPack": (_i, [_vp, _ip, _ip, _u32, _vp, _vp]),
     "lbmHaloUnpack": (_i, [_vp, _ip, _ip, _u32, _u32, _vp, _vp]),
     "lbmHaloCopyPeer": (_i, [_vp, _ip, _vp, _ip, _ip, _u32, _vp]),
+    "lbmCommAddFace": (_i, [_vp, _i, _ip, _ip, _ip, _ip, _i, _ip]),
+    "lbmCommFaceCount": (_i, [_vp, _ip]),
+    "lbmCommGetIpcHandle": (_i, [_vp, _i, _vp]),
+    "lbmCommConnectIpc": (_i, [_vp, _i, _vp]),
+    "lbmCommConnectLocal": (_i, [_vp, _i, _vp, _i]),
+    "lbmCommBeginSync": (_i, [_vp, _i]),
+    "lbmCommPush": (_i, [_vp, _i, _i]),
+    "lbmCommPull": (_i, [_vp, _i, _i]),
+    "lbmCommSync": (_i, [_vp, _i]),
+    "lbmCommStep": (_i, [_vp]),
     "lbmStepShell": (_i, [_vp, _i]),
     "lbmStepInterior": (_i, [_vp, _i]),
     "lbmStreamWaitStream": (_i, [_vp, _i]),

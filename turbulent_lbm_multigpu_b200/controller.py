@@ -12,7 +12,11 @@ by the CUDA C ABI and the host-staged MPI exchange by three interchangeable sync
   "device"  device-side pack kernel -> NCCL send/recv on device buffers -> unpack kernel,
             one grouped exchange per axis phase, minimal 5-slot payload;
   "overlap" like "device", but the step is split: shell kernels first, then the exchange on
-            the comm stream runs concurrently with the interior kernel.
+            the comm stream runs concurrently with the interior kernel;
+  "p2p"     one-sided exchange over NVLink peer memory (CUDA IPC between processes): the push
+            kernel packs a face and stores it straight into the neighbour's staging block and
+            raises a flag, the neighbour waits on the flag on the device and unpacks; the whole
+            overlapped step is ONE call into the library (lbmCommStep) -- no NCCL, no host sync.
 """
 from __future__ import annotations
 
@@ -154,6 +158,25 @@ class CController:
             self._comm_stream = torch.cuda.ExternalStream(comm, device=torch.device("cuda", self.device))
         return self._comm_stream
 
+    def connectFaces(self):
+        """p2p mode: register every CComm as a face, exchange the CUDA-IPC handles of the receive
+        blocks with the neighbours (torch.distributed object gather) and map them."""
+        s = self.cLbmPtr
+        self._face_ids = [s.commAddFace(c, self.slots) for c in self._comm_container]
+        mine = {}
+        for c, fid in zip(self._comm_container, self._face_ids):
+            mine[(self._UID, c.getDstId(), c.axis, c.getCommDirection()[c.axis])] = s.commIpcHandle(fid)
+        dist = self.backend.dist
+        gathered = [None] * self.backend.world
+        dist.all_gather_object(gathered, mine, group=self.backend.group)
+        table = {}
+        for g in gathered:
+            table.update(g)
+        for c, fid in zip(self._comm_container, self._face_ids):
+            key = (c.getDstId(), self._UID, c.axis, -c.getCommDirection()[c.axis])
+            s.commConnectIpc(fid, table[key])
+        dist.barrier(group=self.backend.group)
+
     def ghost_faces(self):
         m = 0
         for a in range(3):
@@ -162,9 +185,17 @@ class CController:
                     m |= 1 << (2 * a + side)
         return m
 
+    def _p2p_sync(self, kind):
+        s = self.cLbmPtr
+        s.commWaitCompute()
+        s.commSync(kind)
+        s.computeWaitComm()
+
     def syncAlpha(self):
         if self.sync_mode == "host":
             self._host_sync(beta=False)
+        elif self.sync_mode == "p2p":
+            self._p2p_sync(capi.LBM_SYNC_ALPHA)
         else:
             s = self.cLbmPtr
             s.commWaitCompute()
@@ -174,6 +205,8 @@ class CController:
     def syncBeta(self):
         if self.sync_mode == "host":
             self._host_sync(beta=True)
+        elif self.sync_mode == "p2p":
+            self._p2p_sync(capi.LBM_SYNC_BETA)
         else:
             s = self.cLbmPtr
             s.commWaitCompute()
@@ -183,6 +216,9 @@ class CController:
     def computeNextStep(self):
         """reference src/CController.hpp:385-391."""
         s = self.cLbmPtr
+        if self.sync_mode == "p2p":
+            s.commStep()                    # shell -> (push/pull || interior) -> join, in the library
+            return
         if self.sync_mode == "overlap" and self._comm_container:
             faces = self.ghost_faces()
             beta_step = (s.simulation_step_counter & 1) == 0
@@ -335,6 +371,8 @@ class CManager:
             self._lbm_controller.addCommunication(c)
         if coords[1] == self._subdomain_nums[1] - 1:
             self._lbm_controller.setGeometry()
+        if self._lbm_controller.sync_mode == "p2p":
+            self._lbm_controller.connectFaces()
 
     def startSimulation(self, **kw):
         if self._lbm_controller is None:
@@ -355,10 +393,12 @@ class InProcessSimulation:
     (pack + send + unpack fused, NVLink peer stores when the devices differ)."""
 
     def __init__(self, domain: CDomain, subdomainNums, devices=None, slots=capi.LBM_HALO_SLOTS_MINIMAL,
-                 **controller_kw):
+                 transport="copy", overlap=False, **controller_kw):
         self.nums = tuple(int(v) for v in subdomainNums)
         self.nranks = self.nums[0] * self.nums[1] * self.nums[2]
         self.slots = slots
+        self.transport = transport      # "copy": one peer-copy kernel per face + host phase sync
+        self.overlap = overlap          # "p2p": push/flag/pull faces, no host synchronisation
         self.controllers = []
         for r in range(self.nranks):
             kw = dict(controller_kw)
@@ -368,6 +408,35 @@ class InProcessSimulation:
             m.initSimulation(r)
             self.controllers.append(m.getController())
         self.sub_size = m.getSubdomainSize()
+        if transport == "p2p":
+            self._connect_local()
+
+    def _connect_local(self):
+        ids = {}
+        for ctrl in self.controllers:
+            s = ctrl.getSolver()
+            for c in ctrl.getComms():
+                ids[(ctrl.getUid(), c.getDstId(), c.axis, c.getCommDirection()[c.axis])] = s.commAddFace(c, self.slots)
+        for ctrl in self.controllers:
+            s = ctrl.getSolver()
+            for c in ctrl.getComms():
+                d = c.getCommDirection()[c.axis]
+                fid = ids[(ctrl.getUid(), c.getDstId(), c.axis, d)]
+                pid = ids[(c.getDstId(), ctrl.getUid(), c.axis, -d)]
+                s.commConnectLocal(fid, self.controllers[c.getDstId()].getSolver(), pid)
+
+    def _sync_p2p(self, beta):
+        """Every push of an axis is enqueued before any wait of that axis, so the device-side
+        flag waits can never be ordered ahead of the push they wait for."""
+        kind = capi.LBM_SYNC_BETA if beta else capi.LBM_SYNC_ALPHA
+        solvers = [c.getSolver() for c in self.controllers]
+        for s in solvers:
+            s.commBeginSync(kind)
+        for axis in range(3):
+            for s in solvers:
+                s.commPush(kind, axis)
+            for s in solvers:
+                s.commPull(kind, axis)
 
     def _sync(self, beta):
         kind = capi.LBM_SYNC_BETA if beta else capi.LBM_SYNC_ALPHA
@@ -393,15 +462,33 @@ class InProcessSimulation:
                     ctrl.getSolver().wait()
 
     def computeNextStep(self):
-        for ctrl in self.controllers:
-            ctrl.getSolver().simulationStep()
-        for ctrl in self.controllers:
-            ctrl.getSolver().wait()
-        self._sync(beta=bool(self.controllers[0].getSolver().simulation_step_counter & 1))
+        solvers = [c.getSolver() for c in self.controllers]
+        if self.transport == "p2p":
+            beta_step = (solvers[0].simulation_step_counter & 1) == 0
+            if self.overlap:
+                for ctrl, s in zip(self.controllers, solvers):
+                    s.stepShell(ctrl.ghost_faces())
+                    s.commWaitCompute()
+                    s.stepInterior(ctrl.ghost_faces())
+            else:
+                for s in solvers:
+                    s.simulationStep()
+                    s.commWaitCompute()
+            self._sync_p2p(beta=beta_step)
+            for s in solvers:
+                s.computeWaitComm()
+            return
+        for s in solvers:
+            s.simulationStep()
+        for s in solvers:
+            s.wait()
+        self._sync(beta=bool(solvers[0].simulation_step_counter & 1))
 
     def run(self, loops):
         for _ in range(loops):
             self.computeNextStep()
+        for ctrl in self.controllers:
+            ctrl.getSolver().wait()
 
 
 def validation_domain_size(domain_size, subdomain_num):

@@ -24,8 +24,22 @@ struct Box { int x0, nx, y0, ny, z0, nz; };
 
 } // namespace
 
+struct lbm_face {
+	int dst_rank;
+	int send_origin[3], recv_origin[3], size[3], dir[3];
+	int axis;
+	uint32_t send_mask[2], recv_mask[2], write_mask[2];   /* per sync kind (alpha, beta) */
+	size_t stage_off[2], stage_elems[2];                  /* layout of the RECEIVER block I own */
+	size_t peer_stage_off[2];                             /* layout of the block I write into */
+	char *local_block; size_t local_bytes;                /* [flags 256 B][alpha staging][beta staging] */
+	char *peer_block; bool peer_is_ipc; bool connected;
+	unsigned int *block_counter;                          /* device, for the push kernel */
+};
+
 struct lbm_solver {
 	lbm_desc desc;
+	std::vector<lbm_face> faces;
+	unsigned int sync_seq[2];
 	int device;
 	int dtype;
 	int sx, sy, sz;
@@ -359,6 +373,7 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	h->dd = h->velocity = h->density = NULL; h->flags = NULL;
 	h->staging = NULL; h->staging_bytes = 0; h->d_checksum = NULL;
 	h->counter = 0; h->launches = 0;
+	h->sync_seq[0] = h->sync_seq[1] = 0;
 	h->smag = d->smagorinsky_cs != 0.0;
 	h->u_lid = d->u_lid;
 	const int maxvec = d->dtype == LBM_F32 ? 4 : 2;
@@ -405,6 +420,11 @@ int lbmDestroy(lbm_t h)
 	cudaSetDevice(h->device);
 	if (h->compute) cudaStreamSynchronize(h->compute);
 	if (h->comm) cudaStreamSynchronize(h->comm);
+	for (size_t i = 0; i < h->faces.size(); i++) {
+		lbm_face &f = h->faces[i];
+		if (f.peer_is_ipc && f.peer_block) cudaIpcCloseMemHandle(f.peer_block);
+		cudaFree(f.local_block); cudaFree(f.block_counter);
+	}
 	cudaFree(h->dd); cudaFree(h->flags); cudaFree(h->velocity); cudaFree(h->density);
 	cudaFree(h->staging); cudaFree(h->d_checksum);
 	if (h->ev_compute) cudaEventDestroy(h->ev_compute);
@@ -724,6 +744,234 @@ int lbmHaloCopyPeer(lbm_t src, const int src_origin[3], lbm_t dst, const int dst
 	launch_rect_bytes(src, src->elem, src->dd, dst->dd, R, stream ? (cudaStream_t)stream : src->comm);
 	CUDA_TRY(src, cudaGetLastError());
 	return LBM_OK;
+}
+
+/* ---------------------------------------------------------------- peer-memory halo exchange */
+namespace {
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+uint32_t slot_mask(int kind, const int dir[3], int slots)
+{
+	uint32_t m = 0;
+	lbmHaloSlotMask(kind, dir, slots, &m);
+	return m;
+}
+
+int face_check(lbm_t h, int face_id)
+{
+	if (face_id < 0 || face_id >= (int)h->faces.size()) return fail(h, LBM_ERR_INVALID, "invalid face id");
+	return LBM_OK;
+}
+
+int face_push(lbm_t h, lbm_face &f, int kind, cudaStream_t s)
+{
+	if (!f.connected) return fail(h, LBM_ERR_INVALID, "halo face is not connected to its peer");
+	const int *origin = kind == LBM_SYNC_BETA ? f.recv_origin : f.send_origin;
+	int field[19], packed[19], n = 0;
+	for (int k = 0; k < 19; k++) if ((f.send_mask[kind] >> k) & 1) { field[n] = k; packed[n] = n; n++; }
+	if (n == 0) return LBM_OK;
+	const RectCopy R = rect_desc(h, origin, f.size, true, field, packed, n);
+	const long long total = (long long)f.size[0] * f.size[1] * f.size[2] * n;
+	long long grid = (total + 255) / 256;
+	if (grid > 148LL * 4) grid = 148LL * 4;
+	volatile unsigned int *flag = (volatile unsigned int *)(f.peer_block + 64 * kind);
+	char *stage = f.peer_block + f.peer_stage_off[kind];
+	if (h->dtype == LBM_F32)
+		halo_push_kernel<float><<<(unsigned)grid, 256, 0, s>>>((const float *)h->dd, (float *)stage, R,
+				f.block_counter, flag, h->sync_seq[kind]);
+	else
+		halo_push_kernel<double><<<(unsigned)grid, 256, 0, s>>>((const double *)h->dd, (double *)stage, R,
+				f.block_counter, flag, h->sync_seq[kind]);
+	h->launches++;
+	CUDA_TRY(h, cudaGetLastError());
+	return LBM_OK;
+}
+
+int face_pull(lbm_t h, lbm_face &f, int kind, cudaStream_t s)
+{
+	const int *origin = kind == LBM_SYNC_BETA ? f.send_origin : f.recv_origin;
+	int field[19], packed[19], n = 0, pos = 0;
+	for (int k = 0; k < 19; k++) {
+		if (!((f.recv_mask[kind] >> k) & 1)) continue;
+		if ((f.write_mask[kind] >> k) & 1) { field[n] = k; packed[n] = pos; n++; }
+		pos++;
+	}
+	halo_wait_kernel<<<1, 1, 0, s>>>((volatile unsigned int *)(f.local_block + 64 * kind), h->sync_seq[kind]);
+	h->launches++;
+	if (n > 0) {
+		const RectCopy R = rect_desc(h, origin, f.size, false, field, packed, n);
+		launch_rect_bytes(h, h->elem, f.local_block + f.stage_off[kind], h->dd, R, s);
+	}
+	CUDA_TRY(h, cudaGetLastError());
+	return LBM_OK;
+}
+
+int ghost_mask_of_faces(lbm_t h)
+{
+	int m = 0;
+	for (size_t i = 0; i < h->faces.size(); i++) {
+		const lbm_face &f = h->faces[i];
+		m |= 1 << (2 * f.axis + (f.dir[f.axis] > 0 ? 0 : 1));
+	}
+	return m;
+}
+
+} // namespace
+
+int lbmCommAddFace(lbm_t h, int dst_rank, const int send_origin[3], const int recv_origin[3], const int size[3],
+		const int dir[3], int slots, int *face_id)
+{
+	CHECK_HANDLE(h);
+	if (!send_origin || !recv_origin || !size || !dir) return fail(h, LBM_ERR_INVALID, "null argument");
+	if (int rc = use_device(h)) return rc;
+	if (int rc = check_rect(h, send_origin, size)) return rc;
+	if (int rc = check_rect(h, recv_origin, size)) return rc;
+	lbm_face f;
+	memset(&f, 0, sizeof(f));
+	f.dst_rank = dst_rank;
+	int nz = 0;
+	for (int a = 0; a < 3; a++) {
+		f.send_origin[a] = send_origin[a]; f.recv_origin[a] = recv_origin[a]; f.size[a] = size[a]; f.dir[a] = dir[a];
+		if (dir[a] != 0) { f.axis = a; nz++; }
+	}
+	if (nz != 1) return fail(h, LBM_ERR_INVALID, "comm direction must be a signed unit vector");
+	const int opp[3] = { -dir[0], -dir[1], -dir[2] };
+	const size_t cells = (size_t)size[0] * size[1] * size[2];
+	size_t off = 256, poff = 256;
+	for (int k = 0; k < 2; k++) {
+		f.recv_mask[k] = slot_mask(k, dir, slots);
+		f.send_mask[k] = slot_mask(k, opp, slots);
+		f.write_mask[k] = k == LBM_SYNC_BETA ? slot_mask(k, dir, LBM_HALO_SLOTS_MINIMAL) : f.recv_mask[k];
+		f.stage_elems[k] = (size_t)popcount19(f.recv_mask[k]) * cells;
+		f.stage_off[k] = off;
+		off += align256(f.stage_elems[k] * h->elem);
+		f.peer_stage_off[k] = poff;
+		poff += align256((size_t)popcount19(f.send_mask[k]) * cells * h->elem);
+	}
+	f.local_bytes = off;
+	CUDA_TRY(h, cudaMalloc((void **)&f.local_block, f.local_bytes));
+	CUDA_TRY(h, cudaMemset(f.local_block, 0, 256));
+	CUDA_TRY(h, cudaMalloc((void **)&f.block_counter, sizeof(unsigned int)));
+	CUDA_TRY(h, cudaMemset(f.block_counter, 0, sizeof(unsigned int)));
+	h->faces.push_back(f);
+	if (face_id) *face_id = (int)h->faces.size() - 1;
+	return LBM_OK;
+}
+
+int lbmCommFaceCount(lbm_t h, int *count)
+{
+	CHECK_HANDLE(h);
+	if (!count) return fail(h, LBM_ERR_INVALID, "null count");
+	*count = (int)h->faces.size();
+	return LBM_OK;
+}
+
+int lbmCommGetIpcHandle(lbm_t h, int face_id, void *handle64)
+{
+	CHECK_HANDLE(h);
+	if (int rc = face_check(h, face_id)) return rc;
+	if (!handle64) return fail(h, LBM_ERR_INVALID, "null handle buffer");
+	if (int rc = use_device(h)) return rc;
+	cudaIpcMemHandle_t hd;
+	CUDA_TRY(h, cudaIpcGetMemHandle(&hd, h->faces[face_id].local_block));
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	memcpy(handle64, &hd, 64);
+	return LBM_OK;
+}
+
+int lbmCommConnectIpc(lbm_t h, int face_id, const void *peer_handle64)
+{
+	CHECK_HANDLE(h);
+	if (int rc = face_check(h, face_id)) return rc;
+	if (!peer_handle64) return fail(h, LBM_ERR_INVALID, "null handle");
+	if (int rc = use_device(h)) return rc;
+	cudaIpcMemHandle_t hd;
+	memcpy(&hd, peer_handle64, 64);
+	void *p = NULL;
+	CUDA_TRY(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+	lbm_face &f = h->faces[face_id];
+	f.peer_block = (char *)p; f.peer_is_ipc = true; f.connected = true;
+	return LBM_OK;
+}
+
+int lbmCommConnectLocal(lbm_t h, int face_id, lbm_t peer, int peer_face_id)
+{
+	CHECK_HANDLE(h); CHECK_HANDLE(peer);
+	if (int rc = face_check(h, face_id)) return rc;
+	if (peer_face_id < 0 || peer_face_id >= (int)peer->faces.size()) return fail(h, LBM_ERR_INVALID, "invalid peer face id");
+	if (int rc = use_device(h)) return rc;
+	if (h->device != peer->device) {
+		int can = 0;
+		CUDA_TRY(h, cudaDeviceCanAccessPeer(&can, h->device, peer->device));
+		if (!can) return fail(h, LBM_ERR_CUDA, "devices are not NVLink/PCIe peers");
+		cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+		if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+			return fail(h, LBM_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+		cudaGetLastError();
+	}
+	lbm_face &f = h->faces[face_id];
+	const lbm_face &g = peer->faces[peer_face_id];
+	for (int k = 0; k < 2; k++)
+		if (f.send_mask[k] != g.recv_mask[k] || f.size[0] != g.size[0] || f.size[1] != g.size[1] || f.size[2] != g.size[2])
+			return fail(h, LBM_ERR_INVALID, "peer face does not mirror this face");
+	f.peer_block = g.local_block; f.peer_is_ipc = false; f.connected = true;
+	return LBM_OK;
+}
+
+int lbmCommBeginSync(lbm_t h, int sync_kind)
+{
+	CHECK_HANDLE(h);
+	if (sync_kind != LBM_SYNC_ALPHA && sync_kind != LBM_SYNC_BETA) return fail(h, LBM_ERR_INVALID, "bad sync kind");
+	h->sync_seq[sync_kind]++;
+	return LBM_OK;
+}
+
+int lbmCommPush(lbm_t h, int sync_kind, int axis)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	for (size_t i = 0; i < h->faces.size(); i++)
+		if (h->faces[i].axis == axis)
+			if (int rc = face_push(h, h->faces[i], sync_kind, h->comm)) return rc;
+	return LBM_OK;
+}
+
+int lbmCommPull(lbm_t h, int sync_kind, int axis)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	for (size_t i = 0; i < h->faces.size(); i++)
+		if (h->faces[i].axis == axis)
+			if (int rc = face_pull(h, h->faces[i], sync_kind, h->comm)) return rc;
+	return LBM_OK;
+}
+
+int lbmCommSync(lbm_t h, int sync_kind)
+{
+	CHECK_HANDLE(h);
+	if (int rc = lbmCommBeginSync(h, sync_kind)) return rc;
+	/* x, then y, then z: later axes carry the rims the earlier ones delivered
+	 * (the reference's sequential CComm walk, src/CManager.hpp:122-199) */
+	for (int axis = 0; axis < 3; axis++) {
+		if (int rc = lbmCommPush(h, sync_kind, axis)) return rc;
+		if (int rc = lbmCommPull(h, sync_kind, axis)) return rc;
+	}
+	return LBM_OK;
+}
+
+int lbmCommStep(lbm_t h)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	if (h->faces.empty()) return lbmStep(h);
+	const int faces = ghost_mask_of_faces(h);
+	const int kind = (h->counter & 1) ? LBM_SYNC_ALPHA : LBM_SYNC_BETA;   /* the sync that follows this step */
+	if (int rc = lbmStepShell(h, faces)) return rc;
+	if (int rc = lbmStreamWaitStream(h, 1)) return rc;      /* exchange starts once the shell is done ... */
+	if (int rc = lbmStepInterior(h, faces)) return rc;      /* ... and overlaps the interior kernel */
+	if (int rc = lbmCommSync(h, kind)) return rc;
+	return lbmStreamWaitStream(h, 0);                       /* the next step needs the halo */
 }
 
 int lbmGetDevicePointer(lbm_t h, int which, void **ptr, size_t *bytes)

@@ -674,6 +674,56 @@ __global__ void rect_copy_kernel(const T *__restrict__ src, T *__restrict__ dst,
 	}
 }
 
+
+/* ================================================================== peer-memory halo
+ * One-sided halo exchange over NVLink peer memory (same process or CUDA-IPC mapped):
+ *   halo_push_kernel  packs the selected slots of a dd rect and stores them STRAIGHT INTO the
+ *                     neighbour's staging buffer (peer stores: pack + send fused); the last
+ *                     block to finish publishes a sequence number in the neighbour's flag word;
+ *   halo_wait_kernel  one thread spins (acquire, system scope) until the local flag reaches the
+ *                     expected sequence number;
+ *   rect_copy_kernel  then unpacks the local staging buffer into the dd rect.
+ * Replaces storeDensityDistribution -> MPI_Isend/Irecv/Waitall -> setDensityDistribution
+ * (reference src/CController.hpp:265-383). */
+template <typename T>
+__global__ void halo_push_kernel(const T *__restrict__ src, T *__restrict__ peer_staging, const RectCopy R,
+		unsigned int *block_counter, volatile unsigned int *peer_flag, unsigned int seq)
+{
+	const long long cells = (long long)R.block[0] * R.block[1] * R.block[2];
+	const long long total = cells * R.ncomp;
+	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+			t += (long long)gridDim.x * blockDim.x) {
+		const int c = (int)(t / cells);
+		long long r = t - (long long)c * cells;
+		const int k = (int)(r / ((long long)R.block[0] * R.block[1]));
+		r -= (long long)k * R.block[0] * R.block[1];
+		const int j = (int)(r / R.block[0]);
+		const int i = (int)(r - (long long)j * R.block[0]);
+		const long long s = (long long)R.src_comp[c] * R.src_comp_stride + (R.so[0] + i)
+				+ (long long)(R.so[1] + j) * R.ss[0] + (long long)(R.so[2] + k) * R.ss[0] * R.ss[1];
+		peer_staging[t] = src[s];                 /* staging layout [slot][z][y][x] == linear t */
+	}
+	/* publish: every block fences its peer stores, the last one raises the flag */
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned int done = atomicAdd(block_counter, 1u);
+		if (done == gridDim.x - 1) {
+			*block_counter = 0;                   /* ready for the next push of this face */
+			__threadfence_system();
+			*peer_flag = seq;
+			__threadfence_system();
+		}
+	}
+}
+
+__global__ void halo_wait_kernel(volatile unsigned int *flag, unsigned int seq)
+{
+	/* sequence numbers only grow; signed distance tolerates wrap-around */
+	while ((int)(*flag - seq) < 0) { __nanosleep(64); }
+	__threadfence_system();
+}
+
 /* ================================================================== checksum
  * device-side variant of CLbmSolver::getVelocityChecksum: sum over FLUID cells of
  * (ux+uy)+uz, accumulated in double with warp shuffles, one atomic per block. */

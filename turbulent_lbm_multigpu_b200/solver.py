@@ -237,6 +237,41 @@ class CLbmSolver:
         self._ck(self._lib.lbmHaloCopyPeer(self._h, capi.i3(src_origin), dst._h, capi.i3(dst_origin),
                                            capi.i3(size), slot_mask, stream))
 
+    # one-sided peer-memory halo exchange (faces = CComm descriptors)
+    def commAddFace(self, comm, slots=capi.LBM_HALO_SLOTS_MINIMAL):
+        fid = ctypes.c_int()
+        self._ck(self._lib.lbmCommAddFace(self._h, int(comm.getDstId()), capi.i3(comm.getSendOrigin()),
+                                          capi.i3(comm.getRecvOrigin()), capi.i3(comm.getSendSize()),
+                                          capi.i3(comm.getCommDirection()), int(slots), ctypes.byref(fid)))
+        return fid.value
+
+    def commIpcHandle(self, face_id):
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self._lib.lbmCommGetIpcHandle(self._h, int(face_id), buf))
+        return buf.raw
+
+    def commConnectIpc(self, face_id, handle_bytes):
+        buf = ctypes.create_string_buffer(bytes(handle_bytes), 64)
+        self._ck(self._lib.lbmCommConnectIpc(self._h, int(face_id), buf))
+
+    def commConnectLocal(self, face_id, peer, peer_face_id):
+        self._ck(self._lib.lbmCommConnectLocal(self._h, int(face_id), peer._h, int(peer_face_id)))
+
+    def commBeginSync(self, kind):
+        self._ck(self._lib.lbmCommBeginSync(self._h, int(kind)))
+
+    def commPush(self, kind, axis):
+        self._ck(self._lib.lbmCommPush(self._h, int(kind), int(axis)))
+
+    def commPull(self, kind, axis):
+        self._ck(self._lib.lbmCommPull(self._h, int(kind), int(axis)))
+
+    def commSync(self, kind):
+        self._ck(self._lib.lbmCommSync(self._h, int(kind)))
+
+    def commStep(self):
+        self._ck(self._lib.lbmCommStep(self._h))
+
     def stepShell(self, ghost_faces):
         self._ck(self._lib.lbmStepShell(self._h, int(ghost_faces)))
 
