@@ -50,6 +50,7 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.lines = []
+        self.mark_at = 0
         self.proc = None
 
     def start(self):
@@ -66,6 +67,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """start of the timed region: earlier samples (warm-up) are reported separately"""
+        self.mark_at = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -76,7 +81,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        timed = self.lines[self.mark_at:]
+        # a short timed region may see only a couple of 100 ms samples: fall back to every
+        # sample taken under load since the warm-up started
+        for ln in (timed if len(timed) >= 3 else self.lines):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -92,20 +100,34 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def scenario(n_gpus, size=SIZE):
+def decomposition(n_gpus, decomp):
+    """(1,1,n) z-slabs (contiguous faces), the reference's x split, or blocks."""
+    if decomp == "slab-x":
+        return (n_gpus, 1, 1)
+    if decomp == "block":
+        return {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[n_gpus]
+    return (1, 1, n_gpus)
+
+
+def scenario(n_gpus, size=SIZE, scaling="weak", decomp="slab", cs=CS):
     from turbulent_lbm_multigpu_b200.configuration import CConfiguration
     cfg = CConfiguration()
-    cfg.domain_size = (size, size, size * n_gpus)
-    cfg.subdomain_num = (1, 1, n_gpus)
-    # weak scaling keeps the cell length (hence tau, u_lid) constant: benchmark.py:72
-    cfg.domain_length = (0.1, 0.1, 0.1 * n_gpus)
-    cfg.smagorinsky_constant = CS
+    nums = decomposition(n_gpus, decomp)
+    if scaling == "weak":
+        cfg.domain_size = tuple(size * k for k in nums)
+        # weak scaling keeps the cell length (hence tau, u_lid) constant: benchmark.py:72
+        cfg.domain_length = tuple(0.1 * k for k in nums)
+    else:
+        cfg.domain_size = (size, size, size)
+        cfg.domain_length = (0.1, 0.1, 0.1)
+    cfg.subdomain_num = nums
+    cfg.smagorinsky_constant = cs
     cfg.loops = 0
     return cfg
 
 
 # ====================================================================== reference arm
-def cpu_reference(size, budget_s=12.0, threads=None):
+def cpu_reference(size, budget_s=12.0, threads=None, dtype=np.float32):
     """The reference's kernels (oracle/_ref) on the host cores: bounded sample of the workload."""
     from oracle import ref
     from turbulent_lbm_multigpu_b200.skeleton import compute_parameters
@@ -142,12 +164,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cb, ms, steps = cpu_reference(SIZE, budget_s=max(4.0, min(60.0, 0.15 * args.steps)))
+    # the CPU sample is always the 256^3 single-domain cavity (the reference's fp32 build)
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core it may run on
+    cb, ms, steps = cpu_reference(min(args.size, 256), budget_s=max(4.0, min(60.0, 0.15 * args.steps)),
+                                  threads=len(os.sched_getaffinity(0)))
     line = {
         "impl": "reference", "metric": "MLUPS", "value": cb["value"], "unit": "MLUPS", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 2, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "steps": steps, "warmup": 2, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -156,11 +181,21 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n):
-    return {"workload": "lid-driven cavity %d^3 per GPU D3Q19 fp32 Smagorinsky C_s=%g (BASELINE configs[1])" % (SIZE, CS),
-            "global_domain": [SIZE, SIZE, SIZE * n], "subdomain_num": [1, 1, n],
-            "parallelism": "z-slab domain decomposition, 1 process per GPU" if n > 1 else "single GPU",
-            "l2": "working set 1.34 GB per GPU >> 126 MB L2 (no flush needed)"}
+def workload_config(args, n):
+    cfg = scenario(n, args.size, args.scaling, args.decomp, args.cs)
+    sub = [d // k for d, k in zip(cfg.domain_size, cfg.subdomain_num)]
+    elem = 4 if args.dtype == "f32" else 8
+    ws = (19 * elem + 4) * sub[0] * sub[1] * sub[2] / 1e9
+    tag = {(256, "weak", "f32"): " (BASELINE configs[1])", (512, "strong", "f32"): " (BASELINE configs[2])",
+           (512, "weak", "f32"): " (BASELINE configs[3])", (384, "strong", "f64"): " (BASELINE configs[4])"}
+    return {"workload": "lid-driven cavity %d^3 %s D3Q19 %s %s%s" % (
+                args.size, "per GPU" if args.scaling == "weak" else "global", "fp32" if args.dtype == "f32" else "fp64",
+                ("Smagorinsky C_s=%g" % args.cs) if args.cs else "BGK",
+                tag.get((args.size, args.scaling, args.dtype), "")),
+            "global_domain": list(cfg.domain_size), "subdomain_num": list(cfg.subdomain_num),
+            "subdomain_size": sub,
+            "parallelism": ("%s domain decomposition, 1 process per GPU" % args.decomp) if n > 1 else "single GPU",
+            "l2": "working set %.2f GB per GPU >> 126 MB L2 (no flush needed)" % ws}
 
 
 # ====================================================================== GPU arm
@@ -184,37 +219,51 @@ def run_gpu(args):
     from turbulent_lbm_multigpu_b200.controller import CManager
     from turbulent_lbm_multigpu_b200.domain import CDomain
 
-    cfg = scenario(n)
+    np_dtype = np.float32 if args.dtype == "f32" else np.float64
+    elem = np.dtype(np_dtype).itemsize
+    bytes_per_lup = 2 * 19 * elem + 4           # 156 B fp32, 308 B fp64
+    cfg = scenario(n, args.size, args.scaling, args.decomp, args.cs)
     domain = CDomain(-1, cfg.domain_size, (0, 0, 0), cfg.domain_length)
     backend = TorchDistributedBackend() if world > 1 else None
     # the library launches on torch-owned streams so that NCCL (torch.distributed) and a
     # CUDA-graph capture of the two-step cycle see the same stream order
-    compute_stream, comm_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    compute_stream, comm_stream = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
     mgr = CManager(domain, cfg.subdomain_num, backend=backend, device=local, config=cfg,
-                   sync_mode=args.sync if world > 1 else "host", dtype=np.float32,
+                   sync_mode=args.sync if world > 1 else "host", dtype=np_dtype,
                    store_velocity=False, store_density=False,
                    compute_stream=compute_stream.cuda_stream, comm_stream=comm_stream.cuda_stream)
     mgr.initSimulation(rank)
     ctrl = mgr.getController()
     s = ctrl.getSolver()
     cells_global = int(np.prod(cfg.domain_size))
-    cells_local = int(np.prod(mgr.getSubdomainSize()))
+    sub = mgr.getSubdomainSize()
+    cells_local = int(np.prod(sub))
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        if dist is None:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     W, K = max(3, args.warmup), args.steps
     W += W & 1                              # whole beta/alpha cycles
     K += K & 1
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                     # sampled from the warm-up on: the timed region is short
     for _ in range(W):
         ctrl.computeNextStep()
     barrier()
     # launch-bound inner loop: capture the beta+alpha cycle (kernels, stream edges, NCCL
     # send/recv) into one CUDA graph and replay it
     graph, per_cycle = None, 0
-    if world > 1 and args.graph:
+    if args.graph:
         try:
             l0 = s.launchCount()
             graph = torch.cuda.CUDAGraph()
@@ -230,9 +279,8 @@ def run_gpu(args):
                 print("cuda graph capture unavailable (%s): eager launches" % e, file=sys.stderr)
             graph = None
             barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     launches0 = s.launchCount()
     s.timerStart()
     if graph is not None:
@@ -246,11 +294,27 @@ def run_gpu(args):
     barrier()
     launches = (K // 2) * per_cycle if graph is not None else s.launchCount() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms)
     value = cells_global * K / (ms * 1e-3) / 1e6
+
+    # ---- halo exposed vs hidden (N > 1): the same steps without any exchange
+    halo = None
+    if world > 1:
+        for _ in range(4):
+            s.simulationStep()
+        barrier()
+        s.timerStart()
+        for _ in range(K):
+            s.simulationStep()
+        ms_nc = max_over_ranks(s.timerStop())
+        barrier()
+        face_bytes = 0
+        for c in ctrl.getComms():
+            face_bytes += 5 * int(np.prod(c.getSendSize())) * elem
+        halo = {"ms_per_step_no_exchange": ms_nc / K, "ms_per_step": ms / K,
+                "exposed_frac": max(0.0, 1.0 - ms_nc / ms), "hidden_frac": min(1.0, ms_nc / ms),
+                "bytes_sent_per_step_per_gpu": face_bytes,
+                "note": "exposed = 1 - t_step(step kernels only) / t_step(with halo exchange), max over ranks"}
 
     # ---- per-kernel timing (alpha / beta alone), single GPU only: explains the roofline
     kern = {}
@@ -264,80 +328,63 @@ def run_gpu(args):
             for _ in range(reps):
                 fn()
             kms = s.timerStop() / reps
-            kern[name] = {"ms": kms, "GBs": BYTES_PER_LUP_F32 * cells_local / (kms * 1e-3) / 1e9}
+            kern[name] = {"ms": kms, "GBs": bytes_per_lup * cells_local / (kms * 1e-3) / 1e9}
 
-    # ---- end to end through the public host API with HOST buffers every step
-    e2e = None
-    if world == 1:
-        S = SIZE
-        rect = (S - 2, 1, S - 2)
-        lid = torch.full((rect[0] * rect[2],), 4, dtype=torch.int32).pin_memory()
-        probe = torch.empty(19 * S, dtype=torch.float32).pin_memory()
-        lid_np, probe_np = lid.numpy(), probe.numpy()
-        po, ps = (S // 2, 0, S // 2), (1, S, 1)
-        for _ in range(3):
-            s.setFlags(lid_np, (1, S - 2, 1), rect); s.simulationStep(); s.storeDensityDistribution(probe_np, po, ps)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            s.setFlags(lid_np, (1, S - 2, 1), rect)             # H2D: boundary input of the step
-            s.simulationStep()
-            s.storeDensityDistribution(probe_np, po, ps)         # D2H: populations on the centre line
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e = {"value": cells_global * K / dt / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": int(lid_np.nbytes), "d2h_bytes_per_step": int(probe_np.nbytes),
-               "api": "CLbmSolver.setFlags + simulationStep + storeDensityDistribution (pinned host buffers)"}
-    else:
-        # multi-GPU: every rank uploads its lid rect and reads back its probe line each step
-        S = SIZE
-        rect = (S - 2, 1, S - 2)
-        lid_np = torch.full((rect[0] * rect[2],), 4, dtype=torch.int32).pin_memory().numpy()
-        probe_np = torch.empty(19 * S, dtype=torch.float32).pin_memory().numpy()
-        po, ps = (S // 2, 0, S // 2), (1, S, 1)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            s.setFlags(lid_np, (1, S - 2, 1), rect)
-            ctrl.computeNextStep()
-            s.storeDensityDistribution(probe_np, po, ps)
-        barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": cells_global * K / float(t.item()) / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": int(lid_np.nbytes) * n, "d2h_bytes_per_step": int(probe_np.nbytes) * n,
-               "api": "CLbmSolver.setFlags + CController.computeNextStep + storeDensityDistribution"}
+    # ---- end to end through the public host API with HOST buffers every step: each rank
+    # uploads the flags of its lid plane (y = Sy-2; pinned host memory -> device) before the
+    # step and reads the 19 populations of its centre line back after it
+    rect = (sub[0] - 2, 1, sub[2] - 2)
+    ro = (1, sub[1] - 2, 1)
+    lid = torch.empty(rect[0] * rect[2], dtype=torch.int32).pin_memory()
+    lid_np = lid.numpy()
+    s.storeFlags(lid_np, ro, rect)          # re-uploading the current flags leaves the run unchanged
+    probe = torch.empty(19 * sub[1], dtype=torch.float32 if elem == 4 else torch.float64).pin_memory()
+    probe_np = probe.numpy()
+    po, ps = (sub[0] // 2, 0, sub[2] // 2), (1, sub[1], 1)
+    for _ in range(4):
+        s.setFlags(lid_np, ro, rect); ctrl.computeNextStep(); s.storeDensityDistribution(probe_np, po, ps)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        s.setFlags(lid_np, ro, rect)                        # H2D: boundary input of the step
+        ctrl.computeNextStep()
+        s.storeDensityDistribution(probe_np, po, ps)        # D2H: populations on the centre line
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": cells_global * K / dt / 1e6, "unit": "MLUPS",
+           "h2d_bytes_per_step": int(lid_np.nbytes) * n, "d2h_bytes_per_step": int(probe_np.nbytes) * n,
+           "api": "CLbmSolver.setFlags + CController.computeNextStep + storeDensityDistribution (pinned host buffers)"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = BYTES_PER_LUP_F32 * cells_local / (ms * 1e-3 / 1.0) / 1e9   # per GPU, per step
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            if tj.get("cells_per_launch") == cells_local and tj.get("dtype", "f32") == args.dtype:
+                traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
+        achieved = bytes_per_lup * cells_local * K / (ms * 1e-3) / 1e9      # per GPU
         line = {
             "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": n, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(n),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, n),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": BYTES_PER_LUP_F32 * cells_local * K / (ms * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s",
-                         "frac": BYTES_PER_LUP_F32 * cells_local * K / (ms * 1e-3) / 1e9 / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": BYTES_PER_LUP_F32 * cells_local,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_lup * cells_local,
                          "kernels": kern,
-                         "note": "step kernels lbm_alpha_kernel/lbm_beta_kernel alternate; 156 B per "
-                                 "lattice-site update x cells per launch / CUDA-event time"},
+                         "note": "per GPU; step kernels lbm_alpha_kernel/lbm_beta_kernel alternate; %d B per "
+                                 "lattice-site update x cells per launch / CUDA-event time" % bytes_per_lup},
+            "halo": halo,
             "sync_mode": args.sync if world > 1 else None, "cuda_graph": graph is not None,
             "kernel_config": s.config(),
         }
-        del achieved
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cb, _, _ = cpu_reference(SIZE, budget_s=args.cpu_budget)
+                cb, _, _ = cpu_reference(min(args.size, 256), budget_s=args.cpu_budget,
+                                         threads=len(os.sched_getaffinity(0)))
                 line["cpu_baseline"] = cb
             except Exception as e:    # the checker being absent must not hide the GPU result
                 line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "reference",
@@ -355,11 +402,16 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=SIZE, help="cells per axis (per GPU for weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--decomp", default="slab", choices=["slab", "slab-x", "block"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--cs", type=float, default=CS, help="Smagorinsky constant (0 = plain BGK, the reference)")
     ap.add_argument("--sync", default="p2p", choices=["host", "device", "overlap", "p2p"],
                     help="halo transport for N > 1 (p2p: one-sided NVLink peer stores; overlap/device: NCCL)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="capture the 2-step cycle in a CUDA graph (N > 1)")
+    ap.add_argument("--graph", action="store_true", help="capture the 2-step cycle in a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -178,6 +178,7 @@ int lbmCommStep(lbm_t h);
 /* ---- overlap support: the step split into the shell next to ghost faces and the interior.
  *      ghost_faces: bit a*2+s set = face (axis a, side s) has a neighbour. --------------- */
 int lbmStepShell(lbm_t h, int ghost_faces);     /* launches on the compute stream */
+int lbmStepShellComm(lbm_t h, int ghost_faces); /* same, on the comm stream (runs next to the interior) */
 int lbmStepInterior(lbm_t h, int ghost_faces);  /* launches on the compute stream; counter++ */
 int lbmStreamWaitStream(lbm_t h, int waiter_is_comm); /* event edge between the two streams */
 int lbmGetStreams(lbm_t h, void **compute_stream, void **comm_stream);

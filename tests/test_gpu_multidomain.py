@@ -84,3 +84,30 @@ def _unused_comm_tables_match_the_oracle_restatement():
         ocoords, obc, ocomms, oorigin = omulti.rank_layout(r, nums, sub)
         assert coords == ocoords and BC == obc and origin == oorigin
         assert [c.as_tuple() for c in comms] == [c.as_tuple() for c in ocomms]
+
+
+def _device_count():
+    import ctypes
+    n = ctypes.c_int(0)
+    capi.load().lbmGetDeviceCount(ctypes.byref(n))
+    return n.value
+
+
+@pytest.mark.parametrize("transport,overlap", [("copy", False), ("p2p", False), ("p2p", True)])
+def test_decomposed_across_devices(transport, overlap):
+    """The same validate criterion with the sub-domains on DIFFERENT GPUs of the box (peer
+    stores over NVLink); skipped on a single-GPU box."""
+    ndev = _device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    D, nums, steps, L = (32, 32, 48), (1, 2, 2), 41, (0.1, 0.1, 0.1)
+    devices = list(range(min(ndev, 4)))
+    sim = InProcessSimulation(CDomain(-1, D, (0, 0, 0), L), nums, devices=devices, transport=transport,
+                              overlap=overlap, config=_cfg(), dtype=np.float32,
+                              beta_order=capi.LBM_BETA_ORDER_LINEAR)
+    sim.run(steps)
+    make, po = omulti.make_oracle_factory(D, nums, L, dtype=np.float32, variant=1)
+    md = omulti.MultiDomain(D, nums, make, slots="minimal")
+    md.run(steps)
+    for r, ctrl in enumerate(sim.controllers):
+        assert bits_equal(ctrl.getSolver().storeDensityDistribution(), md.ranks[r]["solver"].dd), (r, "dd vs oracle")

@@ -87,6 +87,7 @@ SYMBOLS = {
     "lbmCommSync": (_i, [_vp, _i]),
     "lbmCommStep": (_i, [_vp]),
     "lbmStepShell": (_i, [_vp, _i]),
+    "lbmStepShellComm": (_i, [_vp, _i]),
     "lbmStepInterior": (_i, [_vp, _i]),
     "lbmStreamWaitStream": (_i, [_vp, _i]),
     "lbmGetStreams": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),

@@ -222,9 +222,9 @@ class CController:
         if self.sync_mode == "overlap" and self._comm_container:
             faces = self.ghost_faces()
             beta_step = (s.simulation_step_counter & 1) == 0
-            s.stepShell(faces)              # cells next to ghost faces
-            s.commWaitCompute()             # exchange starts when the shell is done ...
-            s.stepInterior(faces)           # ... and runs next to the interior kernel
+            s.commWaitCompute()             # fork: the comm stream follows the previous step
+            s.stepShellComm(faces)          # cells next to ghost faces, on the comm stream ...
+            s.stepInterior(faces)           # ... next to the interior kernel on the compute stream
             self._device_sync(beta=beta_step)
             s.computeWaitComm()             # the next step needs the halo
             return
@@ -467,8 +467,8 @@ class InProcessSimulation:
             beta_step = (solvers[0].simulation_step_counter & 1) == 0
             if self.overlap:
                 for ctrl, s in zip(self.controllers, solvers):
-                    s.stepShell(ctrl.ghost_faces())
                     s.commWaitCompute()
+                    s.stepShellComm(ctrl.ghost_faces())
                     s.stepInterior(ctrl.ghost_faces())
             else:
                 for s in solvers:

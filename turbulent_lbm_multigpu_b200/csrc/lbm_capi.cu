@@ -50,6 +50,7 @@ struct lbm_solver {
 	void *staging; size_t staging_bytes;
 	double *d_checksum;
 	cudaStream_t compute, comm;
+	cudaStream_t step_aux;       /* non-NULL while the comm stream is forked off the compute stream */
 	bool own_compute, own_comm;
 	cudaEvent_t ev_compute, ev_comm, ev_t0, ev_t1;
 	uint64_t counter;
@@ -95,47 +96,53 @@ StepParams<T> make_params(lbm_t h, const Box &b)
 	P.gx = (T)h->desc.gravitation[0]; P.gy = (T)h->desc.gravitation[1]; P.gz = (T)h->desc.gravitation[2];
 	P.u_lid = (T)h->u_lid;
 	P.x0 = b.x0; P.nx = b.nx; P.y0 = b.y0; P.ny = b.ny; P.z0 = b.z0; P.nz = b.nz;
+	P.zsplit = 0x7fffffff; P.zjump = 0;
 	P.wg = h->wg_quirk;
 	P.store_v = h->desc.store_velocity; P.store_r = h->desc.store_density;
 	return P;
 }
 
 template <typename T, int VEC, bool SMAG, bool STORE>
-void launch_alpha(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStream_t s)
+void launch_alpha(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStream_t s, cudaStream_t)
 {
 	lbm_alpha_kernel<T, VEC, SMAG, STORE><<<grid, block, 0, s>>>(P);
 	h->launches++;
 }
 
 template <typename T, int VEC, bool SMAG, bool STORE>
-void launch_beta(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStream_t s)
+void launch_beta(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStream_t s, cudaStream_t sg)
 {
 	const bool shipped = h->desc.beta_order == LBM_BETA_ORDER_SHIPPED;
-	if (P.wg == 0) {   /* with the work-group quirk live every block takes the general path */
-		if (shipped) lbm_beta_kernel<T, VEC, SMAG, STORE, 0><<<grid, block, 0, s>>>(P);
-		else lbm_beta_kernel<T, VEC, SMAG, STORE, 1><<<grid, block, 0, s>>>(P);
-		h->launches++;
-	}
 	/* general kernel: only z planes whose blocks can reach across the array ends
 	 * (|delta| <= sxy + sx + 1 -> planes 0,1 and sz-2,sz-1), or everything with the quirk */
 	const int zlo_end = P.wg > 0 ? P.sz : 2, zhi_begin = P.wg > 0 ? P.sz : P.sz - 2;
 	int ranges[2][2] = { { P.z0, (P.z0 + P.nz < zlo_end ? P.z0 + P.nz : zlo_end) },
 	                     { (P.z0 > zhi_begin ? P.z0 : zhi_begin), P.z0 + P.nz } };
 	if (ranges[1][0] < ranges[0][1]) ranges[1][0] = ranges[0][1];
-	for (int r = 0; r < 2; r++) {
-		const int z0 = ranges[r][0], z1 = ranges[r][1];
-		if (z1 <= z0) continue;
+	/* both z ranges in ONE launch: grid rows [0, nlo) -> low planes, [nlo, nlo+nhi) -> high planes */
+	const int nlo = ranges[0][1] > ranges[0][0] ? ranges[0][1] - ranges[0][0] : 0;
+	const int nhi = ranges[1][1] > ranges[1][0] ? ranges[1][1] - ranges[1][0] : 0;
+	if (nlo + nhi > 0) {
 		StepParams<T> Q = P;
-		Q.z0 = z0; Q.nz = z1 - z0;
+		if (nlo > 0) { Q.z0 = ranges[0][0]; Q.zsplit = nlo; Q.zjump = ranges[1][0] - (ranges[0][0] + nlo); }
+		else { Q.z0 = ranges[1][0]; }
+		Q.nz = nlo + nhi;
 		dim3 g2(grid.x, (unsigned)Q.nz);
-		if (shipped) lbm_beta_general_kernel<T, VEC, SMAG, STORE, 0><<<g2, block, 0, s>>>(Q);
-		else lbm_beta_general_kernel<T, VEC, SMAG, STORE, 1><<<g2, block, 0, s>>>(Q);
+		if (shipped) lbm_beta_general_kernel<T, VEC, SMAG, STORE, 0><<<g2, block, 0, sg>>>(Q);
+		else lbm_beta_general_kernel<T, VEC, SMAG, STORE, 1><<<g2, block, 0, sg>>>(Q);
+		h->launches++;
+	}
+	/* the vectorised kernel second: when sg is another stream the small wrapping kernel is
+	 * already resident and both run side by side */
+	if (P.wg == 0) {   /* with the work-group quirk live every block takes the general path */
+		if (shipped) lbm_beta_kernel<T, VEC, SMAG, STORE, 0><<<grid, block, 0, s>>>(P);
+		else lbm_beta_kernel<T, VEC, SMAG, STORE, 1><<<grid, block, 0, s>>>(P);
 		h->launches++;
 	}
 }
 
 template <typename T, int VEC>
-int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s)
+int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream_t sg)
 {
 	if (b.nx <= 0 || b.ny <= 0 || b.nz <= 0) return LBM_OK;
 	const StepParams<T> P = make_params<T>(h, b);
@@ -145,10 +152,10 @@ int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s)
 	const bool store = h->desc.store_velocity || h->desc.store_density;
 #define LBM_DISPATCH(FN)                                              \
 	do {                                                              \
-		if (h->smag) { if (store) FN<T, VEC, true, true>(h, P, grid, block, s);   \
-		               else       FN<T, VEC, true, false>(h, P, grid, block, s); }\
-		else         { if (store) FN<T, VEC, false, true>(h, P, grid, block, s);  \
-		               else       FN<T, VEC, false, false>(h, P, grid, block, s); } \
+		if (h->smag) { if (store) FN<T, VEC, true, true>(h, P, grid, block, s, sg);   \
+		               else       FN<T, VEC, true, false>(h, P, grid, block, s, sg); }\
+		else         { if (store) FN<T, VEC, false, true>(h, P, grid, block, s, sg);  \
+		               else       FN<T, VEC, false, false>(h, P, grid, block, s, sg); } \
 	} while (0)
 	if (alpha) LBM_DISPATCH(launch_alpha); else LBM_DISPATCH(launch_beta);
 #undef LBM_DISPATCH
@@ -156,18 +163,21 @@ int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s)
 	return LBM_OK;
 }
 
-int launch_step(lbm_t h, bool alpha, const Box &b, cudaStream_t s)
+/* s: stream of the step kernel; sg: stream of beta's wrapping ("general") kernel -- the two
+ * touch disjoint (slot, location) pairs, so sg may be a stream that runs concurrently with s */
+int launch_step(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream_t sg = NULL)
 {
+	if (!sg) sg = s;
 	if (h->dtype == LBM_F32) {
 		switch (h->vec) {
-		case 4: return launch_step_tv<float, 4>(h, alpha, b, s);
-		case 2: return launch_step_tv<float, 2>(h, alpha, b, s);
-		default: return launch_step_tv<float, 1>(h, alpha, b, s);
+		case 4: return launch_step_tv<float, 4>(h, alpha, b, s, sg);
+		case 2: return launch_step_tv<float, 2>(h, alpha, b, s, sg);
+		default: return launch_step_tv<float, 1>(h, alpha, b, s, sg);
 		}
 	}
 	switch (h->vec) {
-	case 2: return launch_step_tv<double, 2>(h, alpha, b, s);
-	default: return launch_step_tv<double, 1>(h, alpha, b, s);
+	case 2: return launch_step_tv<double, 2>(h, alpha, b, s, sg);
+	default: return launch_step_tv<double, 1>(h, alpha, b, s, sg);
 	}
 }
 
@@ -372,7 +382,7 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	h->elem = d->dtype == LBM_F32 ? 4 : 8;
 	h->dd = h->velocity = h->density = NULL; h->flags = NULL;
 	h->staging = NULL; h->staging_bytes = 0; h->d_checksum = NULL;
-	h->counter = 0; h->launches = 0;
+	h->counter = 0; h->launches = 0; h->step_aux = NULL;
 	h->sync_seq[0] = h->sync_seq[1] = 0;
 	h->smag = d->smagorinsky_cs != 0.0;
 	h->u_lid = d->u_lid;
@@ -397,7 +407,11 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	h->own_compute = d->compute_stream == NULL; h->own_comm = d->comm_stream == NULL;
 	h->compute = (cudaStream_t)d->compute_stream; h->comm = (cudaStream_t)d->comm_stream;
 	if (h->own_compute) CREATE_TRY(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
-	if (h->own_comm) CREATE_TRY(cudaStreamCreateWithFlags(&h->comm, cudaStreamNonBlocking));
+	if (h->own_comm) {
+		int prio_lo = 0, prio_hi = 0;
+		CREATE_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		CREATE_TRY(cudaStreamCreateWithPriority(&h->comm, cudaStreamNonBlocking, prio_hi));
+	}
 	CREATE_TRY(cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreate(&h->ev_t0));
@@ -469,7 +483,13 @@ int lbmStepBeta(lbm_t h)
 {
 	CHECK_HANDLE(h);
 	if (int rc = use_device(h)) return rc;
-	return launch_step(h, false, full_box(h), h->compute);
+	if (h->wg_quirk > 0 || h->sz < 8)
+		return launch_step(h, false, full_box(h), h->compute);
+	/* the wrapping kernel (planes at the array ends) runs on the comm stream NEXT TO the
+	 * vectorised kernel instead of behind it: fork, two launches, join */
+	if (int rc = lbmStreamWaitStream(h, 1)) return rc;
+	if (int rc = launch_step(h, false, full_box(h), h->compute, h->comm)) return rc;
+	return lbmStreamWaitStream(h, 0);
 }
 
 int lbmStep(lbm_t h)
@@ -489,16 +509,27 @@ int lbmSteps(lbm_t h, int nsteps)
 	return LBM_OK;
 }
 
-int lbmStepShell(lbm_t h, int ghost_faces)
+static int step_shell_on(lbm_t h, int ghost_faces, cudaStream_t s)
 {
-	CHECK_HANDLE(h);
 	if (int rc = use_device(h)) return rc;
 	std::vector<Box> shell; Box interior;
 	partition(h, ghost_faces, shell, interior);
 	const bool alpha = (h->counter & 1) != 0;
 	for (size_t i = 0; i < shell.size(); i++)
-		if (int rc = launch_step(h, alpha, shell[i], h->compute)) return rc;
+		if (int rc = launch_step(h, alpha, shell[i], s)) return rc;
 	return LBM_OK;
+}
+
+int lbmStepShell(lbm_t h, int ghost_faces)
+{
+	CHECK_HANDLE(h);
+	return step_shell_on(h, ghost_faces, h->compute);
+}
+
+int lbmStepShellComm(lbm_t h, int ghost_faces)
+{
+	CHECK_HANDLE(h);
+	return step_shell_on(h, ghost_faces, h->comm);
 }
 
 int lbmStepInterior(lbm_t h, int ghost_faces)
@@ -508,7 +539,7 @@ int lbmStepInterior(lbm_t h, int ghost_faces)
 	std::vector<Box> shell; Box interior;
 	partition(h, ghost_faces, shell, interior);
 	const bool alpha = (h->counter & 1) != 0;
-	if (int rc = launch_step(h, alpha, interior, h->compute)) return rc;
+	if (int rc = launch_step(h, alpha, interior, h->compute, h->step_aux)) return rc;
 	h->counter++;
 	return LBM_OK;
 }
@@ -967,11 +998,18 @@ int lbmCommStep(lbm_t h)
 	if (h->faces.empty()) return lbmStep(h);
 	const int faces = ghost_mask_of_faces(h);
 	const int kind = (h->counter & 1) ? LBM_SYNC_ALPHA : LBM_SYNC_BETA;   /* the sync that follows this step */
-	if (int rc = lbmStepShell(h, faces)) return rc;
-	if (int rc = lbmStreamWaitStream(h, 1)) return rc;      /* exchange starts once the shell is done ... */
-	if (int rc = lbmStepInterior(h, faces)) return rc;      /* ... and overlaps the interior kernel */
+	/* fork: the (high-priority) comm stream runs shell -> push -> wait -> unpack while the
+	 * compute stream runs the interior kernel; shell and interior touch disjoint
+	 * (slot, location) pairs (A-A invariant), so they may run concurrently.  The shell is
+	 * enqueued first so that its few blocks are scheduled ahead of the interior's. */
+	if (int rc = lbmStreamWaitStream(h, 1)) return rc;
+	if (int rc = lbmStepShellComm(h, faces)) return rc;
+	h->step_aux = h->comm;                                  /* the comm stream is forked: wrapping kernel there */
+	int rc_int = lbmStepInterior(h, faces);
+	h->step_aux = NULL;
+	if (rc_int) return rc_int;
 	if (int rc = lbmCommSync(h, kind)) return rc;
-	return lbmStreamWaitStream(h, 0);                       /* the next step needs the halo */
+	return lbmStreamWaitStream(h, 0);                       /* join: the next step needs the halo */
 }
 
 int lbmGetDevicePointer(lbm_t h, int which, void **ptr, size_t *bytes)

@@ -23,7 +23,7 @@
 
 /* launch bounds are a tuning knob (registers vs resident warps); see DESIGN.md */
 #if defined(LBM_LB_MAXT) && defined(LBM_LB_MINB)
-#define LBM_LB_ALPHA __launch_bounds__(LBM_LB_MAXT, LBM_LB_MINB)
+#define LBM_LB_ALPHA
 #define LBM_LB_BETA __launch_bounds__(LBM_LB_MAXT, LBM_LB_MINB)
 #else
 #define LBM_LB_ALPHA
@@ -47,6 +47,8 @@ struct StepParams {
 	T gx, gy, gz, u_lid;
 	/* iteration box (cells): x0/nx multiples of VEC */
 	int x0, nx, y0, ny, z0, nz;
+	/* grid rows >= zsplit map to z0 + row + zjump: two z ranges in ONE launch */
+	int zsplit, zjump;
 	int wg;                  /* >0: emulate lbm_beta.cl:221-234 work-group x-shift */
 	int store_v, store_r;    /* write velocity / density arrays (only read when STORE) */
 };
@@ -398,6 +400,13 @@ __device__ __forceinline__ void beta_cell(T (&d)[19], int flag, const StepParams
 	}
 }
 
+template <typename T>
+__device__ __forceinline__ int box_z(const StepParams<T> &P)
+{
+	const int row = (int)blockIdx.y;
+	return P.z0 + row + (row >= P.zsplit ? P.zjump : 0);
+}
+
 /* thread -> first cell of its VEC-wide group inside the iteration box; false = out of box */
 template <typename T, int VEC>
 __device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
@@ -407,7 +416,7 @@ __device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
 	long long off;
 	if (P.nx == P.sx) off = (long long)P.y0 * P.sx + t;
 	else { const int iy = (int)(t / P.nx), ix = (int)(t - (long long)iy * P.nx); off = (long long)(P.y0 + iy) * P.sx + P.x0 + ix; }
-	gid = (long long)(P.z0 + blockIdx.y) * P.sxy + off;
+	gid = (long long)box_z(P) * P.sxy + off;
 	return true;
 }
 
@@ -487,7 +496,7 @@ __device__ __forceinline__ bool beta_block_is_general(const StepParams<T> &P)
 	long long o0, o1;
 	if (P.nx == P.sx) { o0 = (long long)P.y0 * P.sx + t0; o1 = (long long)P.y0 * P.sx + t1; }
 	else { o0 = (long long)(P.y0 + t0 / P.nx) * P.sx; o1 = (long long)(P.y0 + t1 / P.nx) * P.sx + P.sx - 1; }
-	const long long zb = (long long)(P.z0 + blockIdx.y) * P.sxy;
+	const long long zb = (long long)box_z(P) * P.sxy;
 	const long long reach = P.sxy + P.sx + 1;
 	return (zb + o0 < reach) || (zb + o1 + reach >= P.n);
 }

@@ -275,6 +275,10 @@ class CLbmSolver:
     def stepShell(self, ghost_faces):
         self._ck(self._lib.lbmStepShell(self._h, int(ghost_faces)))
 
+    def stepShellComm(self, ghost_faces):
+        """shell kernels on the comm stream: they run next to the interior kernel"""
+        self._ck(self._lib.lbmStepShellComm(self._h, int(ghost_faces)))
+
     def stepInterior(self, ghost_faces):
         self._ck(self._lib.lbmStepInterior(self._h, int(ghost_faces)))
 
