@@ -183,12 +183,16 @@ int lbmStepInterior(lbm_t h, int ghost_faces);  /* launches on the compute strea
 int lbmStreamWaitStream(lbm_t h, int waiter_is_comm); /* event edge between the two streams */
 int lbmGetStreams(lbm_t h, void **compute_stream, void **comm_stream);
 
-/* ---- raw device pointers for zero-copy interop (dd, flags, velocity, density) ---------- */
+/* ---- raw device pointers for zero-copy interop (dd, flags, velocity, density).
+ *      dd is [19][slot_stride] with slot_stride >= cells (lbmGetSlotStride; equal to cells
+ *      unless the tuning hook LBM_B200_SLOT_PAD_BYTES pads it); the host-buffer entry points
+ *      above always use the dense [19][cells] layout of the reference. ---------------------- */
 #define LBM_BUF_DD 0
 #define LBM_BUF_FLAGS 1
 #define LBM_BUF_VELOCITY 2
 #define LBM_BUF_DENSITY 3
 int lbmGetDevicePointer(lbm_t h, int which, void **ptr, size_t *bytes);
+int lbmGetSlotStride(lbm_t h, size_t *cells);
 
 /* ---- timing on the compute stream with CUDA events (replaces CStopwatch around the loop,
  *      src/CController.hpp:429-438) --------------------------------------------------- */

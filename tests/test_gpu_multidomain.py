@@ -93,6 +93,21 @@ def _device_count():
     return n.value
 
 
+@pytest.mark.parametrize("transport,overlap", [("copy", False), ("p2p", True)])
+def test_decomposed_with_padded_slot_stride(transport, overlap, monkeypatch):
+    """halo pack / push / unpack / peer copy with a padded dd slot stride"""
+    monkeypatch.setenv("LBM_B200_SLOT_PAD_BYTES", "4352")
+    D, nums, steps, L = (24, 24, 24), (2, 2, 2), 21, (0.1, 0.1, 0.1)
+    sim = InProcessSimulation(CDomain(-1, D, (0, 0, 0), L), nums, transport=transport, overlap=overlap,
+                              config=_cfg(), dtype=np.float32, beta_order=capi.LBM_BETA_ORDER_LINEAR)
+    sim.run(steps)
+    make, po = omulti.make_oracle_factory(D, nums, L, dtype=np.float32, variant=1)
+    md = omulti.MultiDomain(D, nums, make, slots="minimal")
+    md.run(steps)
+    for r, ctrl in enumerate(sim.controllers):
+        assert bits_equal(ctrl.getSolver().storeDensityDistribution(), md.ranks[r]["solver"].dd), (r, "dd vs oracle")
+
+
 @pytest.mark.parametrize("transport,overlap", [("copy", False), ("p2p", False), ("p2p", True)])
 def test_decomposed_across_devices(transport, overlap):
     """The same validate criterion with the sub-domains on DIFFERENT GPUs of the box (peer

@@ -189,3 +189,34 @@ def test_known_answer_64cubed_100_steps():
     v = c.storeVelocity()
     assert np.float32(v[g]) == np.float32(-0.000478317961)
     assert np.float32(c.storeDensity()[g]) == np.float32(1.0000093)
+
+
+@pytest.mark.parametrize("size,dtype,order", [((40, 24, 16), np.float32, 0), ((16, 16, 16), np.float32, 0),
+                                               ((40, 24, 16), np.float64, 1)])
+def test_padded_slot_stride_is_invisible(size, dtype, order, monkeypatch):
+    """The library pads the slot stride of dd for the big power-of-two domains (L2-slice
+    aliasing); forced on here: steps, whole-array and rect access, halo pack/unpack must be
+    unaffected (host buffers stay dense [19][cells])."""
+    monkeypatch.setenv("LBM_B200_SLOT_PAD_BYTES", "4352")
+    c = make_cuda(size, dtype, order=order)
+    import ctypes
+    stride = ctypes.c_size_t(0)
+    assert c._lib.lbmGetSlotStride(c.handle, ctypes.byref(stride)) == 0
+    assert stride.value == int(np.prod(size)) + 4352 // np.dtype(dtype).itemsize
+    o = make_oracle(size, dtype, order=order)
+    for i in range(7):
+        c.simulationStep()
+        o.simulationStep()
+        assert_state_equal(c, o, ctx="padded step %d" % i)
+    origin, rect = (2, 1, 3), (5, 4, 6)
+    block = c.storeDensityDistribution(origin=origin, size=rect).reshape(19, rect[2], rect[1], rect[0])
+    full = o.dd.reshape(19, size[2], size[1], size[0])
+    assert bits_equal(block, full[:, 3:9, 1:5, 2:7])
+    new = np.arange(19 * 5 * 4 * 6, dtype=dtype) * dtype(1e-3)
+    c.setDensityDistribution(new, origin, rect)
+    got = c.storeDensityDistribution().reshape(19, size[2], size[1], size[0])
+    full2 = full.copy()
+    full2[:, 3:9, 1:5, 2:7] = new.reshape(19, 6, 4, 5)
+    assert bits_equal(got, full2)
+    c.setDensityDistribution(o.dd)          # whole-array upload through the pitched copy
+    assert bits_equal(c.storeDensityDistribution(), o.dd)

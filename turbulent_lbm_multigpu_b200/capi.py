@@ -88,6 +88,7 @@ SYMBOLS = {
     "lbmCommStep": (_i, [_vp]),
     "lbmStepShell": (_i, [_vp, _i]),
     "lbmStepShellComm": (_i, [_vp, _i]),
+    "lbmGetSlotStride": (_i, [_vp, ctypes.POINTER(ctypes.c_size_t)]),
     "lbmStepInterior": (_i, [_vp, _i]),
     "lbmStreamWaitStream": (_i, [_vp, _i]),
     "lbmGetStreams": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),

@@ -44,6 +44,7 @@ struct lbm_solver {
 	int dtype;
 	int sx, sy, sz;
 	long long n;
+	long long stride;            /* slot stride of dd in cells (n + padding) */
 	size_t elem;                 /* sizeof(T) */
 	void *dd, *velocity, *density;
 	int *flags;
@@ -89,7 +90,7 @@ StepParams<T> make_params(lbm_t h, const Box &b)
 {
 	StepParams<T> P;
 	P.dd = (T *)h->dd; P.flags = h->flags; P.velocity = (T *)h->velocity; P.density = (T *)h->density;
-	P.n = h->n; P.sx = h->sx; P.sy = h->sy; P.sz = h->sz; P.sxy = (long long)h->sx * h->sy;
+	P.n = h->n; P.ns = h->stride; P.sx = h->sx; P.sy = h->sy; P.sz = h->sz; P.sxy = (long long)h->sx * h->sy;
 	P.inv_tau = (T)h->desc.inv_tau; P.tau = (T)h->desc.tau;
 	/* smag_k = 18*sqrt(2)*C_s^2 evaluated in double, rounded once to T (oracle/port.py) */
 	P.smag_k = (T)(18.0 * std::sqrt(2.0) * h->desc.smagorinsky_cs * h->desc.smagorinsky_cs);
@@ -262,8 +263,9 @@ void launch_rect_bytes(lbm_t h, size_t elem, const void *src, void *dst, const R
 
 /* field (ncomp_total components of n cells) rect  <->  packed buffer [comp][z][y][x] */
 RectCopy rect_desc(lbm_t h, const int origin[3], const int size[3], bool to_packed,
-		const int *field_comps, const int *packed_comps, int ncomp)
+		const int *field_comps, const int *packed_comps, int ncomp, long long field_stride = 0)
 {
+	if (field_stride == 0) field_stride = h->n;
 	RectCopy R;
 	const long long cells = (long long)size[0] * size[1] * size[2];
 	const int zero[3] = { 0, 0, 0 };
@@ -275,8 +277,8 @@ RectCopy rect_desc(lbm_t h, const int origin[3], const int size[3], bool to_pack
 		R.dorg[a] = to_packed ? zero[a] : origin[a];
 		R.ds[a] = to_packed ? size[a] : S[a];
 	}
-	R.src_comp_stride = to_packed ? h->n : cells;
-	R.dst_comp_stride = to_packed ? cells : h->n;
+	R.src_comp_stride = to_packed ? field_stride : cells;
+	R.dst_comp_stride = to_packed ? cells : field_stride;
 	R.ncomp = ncomp;
 	for (int c = 0; c < ncomp; c++) {
 		R.src_comp[c] = to_packed ? field_comps[c] : packed_comps[c];
@@ -286,12 +288,14 @@ RectCopy rect_desc(lbm_t h, const int origin[3], const int size[3], bool to_pack
 }
 
 int store_field(lbm_t h, const void *field, size_t elem, int comps, void *host_dst,
-		const int origin[3], const int size[3])
+		const int origin[3], const int size[3], long long field_stride = 0)
 {
+	if (field_stride == 0) field_stride = h->n;
 	if (int rc = use_device(h)) return rc;
 	if (!host_dst) return fail(h, LBM_ERR_INVALID, "null host pointer");
 	if (!origin || !size) {
-		CUDA_TRY(h, cudaMemcpyAsync(host_dst, field, (size_t)comps * h->n * elem, cudaMemcpyDeviceToHost, h->compute));
+		CUDA_TRY(h, cudaMemcpy2DAsync(host_dst, (size_t)h->n * elem, field, (size_t)field_stride * elem,
+				(size_t)h->n * elem, comps, cudaMemcpyDeviceToHost, h->compute));
 		CUDA_TRY(h, cudaStreamSynchronize(h->compute));
 		return LBM_OK;
 	}
@@ -300,7 +304,7 @@ int store_field(lbm_t h, const void *field, size_t elem, int comps, void *host_d
 	if (int rc = ensure_staging(h, bytes)) return rc;
 	int ids[19];
 	for (int c = 0; c < comps; c++) ids[c] = c;
-	const RectCopy R = rect_desc(h, origin, size, true, ids, ids, comps);
+	const RectCopy R = rect_desc(h, origin, size, true, ids, ids, comps, field_stride);
 	launch_rect_bytes(h, elem, field, h->staging, R, h->compute);
 	CUDA_TRY(h, cudaGetLastError());
 	CUDA_TRY(h, cudaMemcpyAsync(host_dst, h->staging, bytes, cudaMemcpyDeviceToHost, h->compute));
@@ -309,12 +313,15 @@ int store_field(lbm_t h, const void *field, size_t elem, int comps, void *host_d
 }
 
 int set_field(lbm_t h, void *field, size_t elem, int comps, const void *host_src,
-		const int origin[3], const int size[3], const int *keep /* per component or NULL */)
+		const int origin[3], const int size[3], const int *keep /* per component or NULL */,
+		long long field_stride = 0)
 {
+	if (field_stride == 0) field_stride = h->n;
 	if (int rc = use_device(h)) return rc;
 	if (!host_src) return fail(h, LBM_ERR_INVALID, "null host pointer");
 	if (!origin || !size) {
-		CUDA_TRY(h, cudaMemcpyAsync(field, host_src, (size_t)comps * h->n * elem, cudaMemcpyHostToDevice, h->compute));
+		CUDA_TRY(h, cudaMemcpy2DAsync(field, (size_t)field_stride * elem, host_src, (size_t)h->n * elem,
+				(size_t)h->n * elem, comps, cudaMemcpyHostToDevice, h->compute));
 		CUDA_TRY(h, cudaStreamSynchronize(h->compute));
 		return LBM_OK;
 	}
@@ -325,7 +332,7 @@ int set_field(lbm_t h, void *field, size_t elem, int comps, const void *host_src
 	int ids[19], nsel = 0;
 	for (int c = 0; c < comps; c++) if (!keep || keep[c]) ids[nsel++] = c;
 	if (nsel > 0) {
-		const RectCopy R = rect_desc(h, origin, size, false, ids, ids, nsel);
+		const RectCopy R = rect_desc(h, origin, size, false, ids, ids, nsel, field_stride);
 		launch_rect_bytes(h, elem, h->staging, field, R, h->compute);
 		CUDA_TRY(h, cudaGetLastError());
 	}
@@ -379,6 +386,17 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	h->device = d->device; h->dtype = d->dtype;
 	h->sx = d->size[0]; h->sy = d->size[1]; h->sz = d->size[2];
 	h->n = (long long)h->sx * h->sy * h->sz;
+	{
+		/* slot stride: dense by default.  Padding the stride (to keep the 19 slot streams of a
+		 * warp off one L2 slice / HBM channel group) was measured on B200 at 256^3 and 512^3
+		 * fp32 and 384^3 fp64: 0 B is best, 4 KiB..1 MiB of padding cost 1-2 %
+		 * (profiles/r1_slot_pad_sweep.md) -- the address hash already spreads power-of-two
+		 * strides.  The knob stays as a tuning hook. */
+		long long pad_bytes = 0;
+		if (const char *e = getenv("LBM_B200_SLOT_PAD_BYTES")) pad_bytes = atoll(e);
+		pad_bytes = (pad_bytes + 255) / 256 * 256;
+		h->stride = h->n + pad_bytes / (d->dtype == LBM_F32 ? 4 : 8);
+	}
 	h->elem = d->dtype == LBM_F32 ? 4 : 8;
 	h->dd = h->velocity = h->density = NULL; h->flags = NULL;
 	h->staging = NULL; h->staging_bytes = 0; h->d_checksum = NULL;
@@ -416,7 +434,8 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	CREATE_TRY(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreate(&h->ev_t0));
 	CREATE_TRY(cudaEventCreate(&h->ev_t1));
-	CREATE_TRY(cudaMalloc(&h->dd, (size_t)19 * h->n * h->elem));
+	CREATE_TRY(cudaMalloc(&h->dd, (size_t)19 * h->stride * h->elem));
+	CREATE_TRY(cudaMemsetAsync(h->dd, 0, (size_t)19 * h->stride * h->elem, h->compute));
 	CREATE_TRY(cudaMalloc((void **)&h->flags, (size_t)h->n * sizeof(int)));
 	CREATE_TRY(cudaMalloc((void **)&h->d_checksum, sizeof(double)));
 	if (d->store_velocity) { CREATE_TRY(cudaMalloc(&h->velocity, (size_t)3 * h->n * h->elem)); }
@@ -461,11 +480,11 @@ int lbmReset(lbm_t h)
 	const int *bc = h->desc.bc;
 	if (h->dtype == LBM_F32)
 		lbm_init_kernel<float><<<grid, block, 0, h->compute>>>((float *)h->dd, h->flags, (float *)h->velocity,
-				(float *)h->density, h->n, h->sx, h->sy, h->sz, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5],
+				(float *)h->density, h->n, h->stride, h->sx, h->sy, h->sz, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5],
 				h->velocity != NULL, h->density != NULL);
 	else
 		lbm_init_kernel<double><<<grid, block, 0, h->compute>>>((double *)h->dd, h->flags, (double *)h->velocity,
-				(double *)h->density, h->n, h->sx, h->sy, h->sz, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5],
+				(double *)h->density, h->n, h->stride, h->sx, h->sy, h->sz, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5],
 				h->velocity != NULL, h->density != NULL);
 	h->launches++;
 	CUDA_TRY(h, cudaGetLastError());
@@ -590,7 +609,7 @@ int lbmSetDrivenCavityVelocity(lbm_t h, double u_lid) { CHECK_HANDLE(h); h->u_li
 int lbmStoreDD(lbm_t h, void *host_dst, const int origin[3], const int size[3])
 {
 	CHECK_HANDLE(h);
-	return store_field(h, h->dd, h->elem, 19, host_dst, origin, size);
+	return store_field(h, h->dd, h->elem, 19, host_dst, origin, size, h->stride);
 }
 
 int lbmSetDD(lbm_t h, const void *host_src, const int origin[3], const int size[3], const int norm[3])
@@ -599,7 +618,7 @@ int lbmSetDD(lbm_t h, const void *host_src, const int origin[3], const int size[
 	int keep[19];
 	for (int f = 0; f < 19; f++)   /* src/CLbmSolver.hpp:748: norm.dotProd(lbm_units[f]) > 0 */
 		keep[f] = !norm || (norm[0] * kUnits[f][0] + norm[1] * kUnits[f][1] + norm[2] * kUnits[f][2] > 0);
-	return set_field(h, h->dd, h->elem, 19, host_src, origin, size, keep);
+	return set_field(h, h->dd, h->elem, 19, host_src, origin, size, keep, h->stride);
 }
 
 int lbmStoreVelocity(lbm_t h, void *host_dst, const int origin[3], const int size[3])
@@ -717,7 +736,7 @@ int lbmHaloPack(lbm_t h, const int origin[3], const int size[3], uint32_t slot_m
 	int field[19], packed[19], n = 0;
 	for (int f = 0; f < 19; f++) if ((slot_mask >> f) & 1) { field[n] = f; packed[n] = n; n++; }
 	if (n == 0) return LBM_OK;
-	const RectCopy R = rect_desc(h, origin, size, true, field, packed, n);
+	const RectCopy R = rect_desc(h, origin, size, true, field, packed, n, h->stride);
 	launch_rect_bytes(h, h->elem, h->dd, dev_buf, R, stream ? (cudaStream_t)stream : h->comm);
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
@@ -738,7 +757,7 @@ int lbmHaloUnpack(lbm_t h, const int origin[3], const int size[3], uint32_t buf_
 		pos++;
 	}
 	if (n == 0) return LBM_OK;
-	const RectCopy R = rect_desc(h, origin, size, false, field, packed, n);
+	const RectCopy R = rect_desc(h, origin, size, false, field, packed, n, h->stride);
 	launch_rect_bytes(h, h->elem, dev_buf, h->dd, R, stream ? (cudaStream_t)stream : h->comm);
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
@@ -767,7 +786,7 @@ int lbmHaloCopyPeer(lbm_t src, const int src_origin[3], lbm_t dst, const int dst
 	for (int a = 0; a < 3; a++) {
 		R.block[a] = size[a]; R.so[a] = src_origin[a]; R.ss[a] = S[a]; R.dorg[a] = dst_origin[a]; R.ds[a] = D[a];
 	}
-	R.src_comp_stride = src->n; R.dst_comp_stride = dst->n;
+	R.src_comp_stride = src->stride; R.dst_comp_stride = dst->stride;
 	int n = 0;
 	for (int f = 0; f < 19; f++) if ((slot_mask >> f) & 1) { R.src_comp[n] = f; R.dst_comp[n] = f; n++; }
 	R.ncomp = n;
@@ -802,7 +821,7 @@ int face_push(lbm_t h, lbm_face &f, int kind, cudaStream_t s)
 	int field[19], packed[19], n = 0;
 	for (int k = 0; k < 19; k++) if ((f.send_mask[kind] >> k) & 1) { field[n] = k; packed[n] = n; n++; }
 	if (n == 0) return LBM_OK;
-	const RectCopy R = rect_desc(h, origin, f.size, true, field, packed, n);
+	const RectCopy R = rect_desc(h, origin, f.size, true, field, packed, n, h->stride);
 	const long long total = (long long)f.size[0] * f.size[1] * f.size[2] * n;
 	long long grid = (total + 255) / 256;
 	if (grid > 148LL * 4) grid = 148LL * 4;
@@ -831,7 +850,7 @@ int face_pull(lbm_t h, lbm_face &f, int kind, cudaStream_t s)
 	halo_wait_kernel<<<1, 1, 0, s>>>((volatile unsigned int *)(f.local_block + 64 * kind), h->sync_seq[kind]);
 	h->launches++;
 	if (n > 0) {
-		const RectCopy R = rect_desc(h, origin, f.size, false, field, packed, n);
+		const RectCopy R = rect_desc(h, origin, f.size, false, field, packed, n, h->stride);
 		launch_rect_bytes(h, h->elem, f.local_block + f.stage_off[kind], h->dd, R, s);
 	}
 	CUDA_TRY(h, cudaGetLastError());
@@ -1018,13 +1037,21 @@ int lbmGetDevicePointer(lbm_t h, int which, void **ptr, size_t *bytes)
 	if (!ptr) return fail(h, LBM_ERR_INVALID, "null ptr");
 	size_t b = 0;
 	switch (which) {
-	case LBM_BUF_DD: *ptr = h->dd; b = (size_t)19 * h->n * h->elem; break;
+	case LBM_BUF_DD: *ptr = h->dd; b = (size_t)19 * h->stride * h->elem; break;
 	case LBM_BUF_FLAGS: *ptr = h->flags; b = (size_t)h->n * sizeof(int); break;
 	case LBM_BUF_VELOCITY: *ptr = h->velocity; b = h->velocity ? (size_t)3 * h->n * h->elem : 0; break;
 	case LBM_BUF_DENSITY: *ptr = h->density; b = h->density ? (size_t)h->n * h->elem : 0; break;
 	default: return fail(h, LBM_ERR_INVALID, "unknown buffer id");
 	}
 	if (bytes) *bytes = b;
+	return LBM_OK;
+}
+
+int lbmGetSlotStride(lbm_t h, size_t *cells)
+{
+	CHECK_HANDLE(h);
+	if (!cells) return fail(h, LBM_ERR_INVALID, "null cells");
+	*cells = (size_t)h->stride;
 	return LBM_OK;
 }
 

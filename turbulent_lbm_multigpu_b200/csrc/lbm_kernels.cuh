@@ -41,6 +41,8 @@ struct StepParams {
 	T *velocity;
 	T *density;
 	long long n;             /* cells */
+	long long ns;            /* slot stride of dd in cells (>= n; padded so that the 19 slot
+	                            streams of a warp do not alias onto one L2 slice / HBM channel) */
 	int sx, sy, sz;
 	long long sxy;
 	T inv_tau, tau, smag_k;
@@ -441,7 +443,7 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 	T v[19][VEC];
 	T *base = P.dd + gid;
 #pragma unroll
-	for (int i = 0; i < 19; i++) VecIO<T, VEC>::load(base + (long long)i * P.n, v[i]);
+	for (int i = 0; i < 19; i++) VecIO<T, VEC>::load(base + (long long)i * P.ns, v[i]);
 
 	T orho[VEC], ovx[VEC], ovy[VEC], ovz[VEC];
 #pragma unroll
@@ -461,8 +463,8 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 	}
 	if (any_write) {
 #pragma unroll
-		for (int i = 0; i < 18; i++) VecIO<T, VEC>::store(base + (long long)i * P.n, v[i ^ 1]);
-		VecIO<T, VEC>::store(base + 18LL * P.n, v[18]);
+		for (int i = 0; i < 18; i++) VecIO<T, VEC>::store(base + (long long)i * P.ns, v[i ^ 1]);
+		VecIO<T, VEC>::store(base + 18LL * P.ns, v[18]);
 	}
 	if (STORE) {
 #pragma unroll
@@ -525,7 +527,7 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	loc[14] = base + DY - DZ;     loc[15] = base - DY + DZ;
 	loc[16] = base + DZ;          loc[17] = base - DZ;
 #pragma unroll
-	for (int i = 0; i < 18; i++) loc[i] += (long long)i * P.n;
+	for (int i = 0; i < 18; i++) loc[i] += (long long)i * P.ns;
 
 	T v[19][VEC];
 #pragma unroll
@@ -534,7 +536,7 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 		if (shifted) VecIO<T, VEC>::load_shifted(loc[i], v[i ^ 1]);
 		else VecIO<T, VEC>::load(loc[i], v[i ^ 1]);
 	}
-	VecIO<T, VEC>::load(base + 18LL * P.n, v[18]);
+	VecIO<T, VEC>::load(base + 18LL * P.ns, v[18]);
 
 	T orho[VEC], ovx[VEC], ovy[VEC], ovz[VEC];
 #pragma unroll
@@ -552,7 +554,7 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 		if (shifted) VecIO<T, VEC>::store_shifted(loc[i], v[i]);
 		else VecIO<T, VEC>::store(loc[i], v[i]);
 	}
-	VecIO<T, VEC>::store(base + 18LL * P.n, v[18]);
+	VecIO<T, VEC>::store(base + 18LL * P.ns, v[18]);
 
 	if (STORE) {
 #pragma unroll
@@ -599,17 +601,17 @@ __global__ void lbm_beta_general_kernel(const StepParams<T> P)
 		for (int i = 0; i < 18; i++) {
 			while (L[i] < 0) L[i] += P.n;
 			while (L[i] >= P.n) L[i] -= P.n;
-			L[i] += (long long)i * P.n;
+			L[i] += (long long)i * P.ns;
 		}
 		T d[19];
 #pragma unroll
 		for (int i = 0; i < 18; i++) d[i ^ 1] = P.dd[L[i]];
-		d[18] = P.dd[18LL * P.n + c];
+		d[18] = P.dd[18LL * P.ns + c];
 		T rho, vx, vy, vz;
 		beta_cell<T, SMAG, ORDER>(d, flag, P, rho, vx, vy, vz);
 #pragma unroll
 		for (int i = 0; i < 18; i++) P.dd[L[i]] = d[i];
-		P.dd[18LL * P.n + c] = d[18];
+		P.dd[18LL * P.ns + c] = d[18];
 		if (STORE && flag != FLAG_GHOST) {
 			if (P.store_v) { P.velocity[c] = vx; P.velocity[P.n + c] = vy; P.velocity[2 * P.n + c] = vz; }
 			if (P.store_r) P.density[c] = rho;
@@ -621,7 +623,7 @@ __global__ void lbm_beta_general_kernel(const StepParams<T> P)
  * lbm_init.cl:32-237 */
 template <typename T>
 __global__ void lbm_init_kernel(T *dd, int *flags, T *velocity, T *density,
-		long long n, int sx, int sy, int sz, int b0, int b1, int b2, int b3, int b4, int b5,
+		long long n, long long ns, int sx, int sy, int sz, int b0, int b1, int b2, int b3, int b4, int b5,
 		int store_v, int store_r)
 {
 	const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -642,7 +644,7 @@ __global__ void lbm_init_kernel(T *dd, int *flags, T *velocity, T *density,
 	const T p = rho - (T)(3.0f / 2.0f) * (vx * vx);       /* :133-134 */
 	equilibria(eq, vx, vy, vz, p);
 #pragma unroll
-	for (int i = 0; i < 19; i++) dd[(long long)i * n + gid] = eq[i];
+	for (int i = 0; i < 19; i++) dd[(long long)i * ns + gid] = eq[i];
 	flags[gid] = flag;
 	if (store_v) { velocity[gid] = vx; velocity[n + gid] = vy; velocity[2 * n + gid] = vz; }
 	if (store_r) density[gid] = rho;
