@@ -159,7 +159,7 @@ def test_cpp_decomposed_velocity_equals_oracle(exe, tmp_path, sync):
         n = int(hdr[1]) * int(hdr[2]) * int(hdr[3])
         vel = np.frombuffer(raw, np.float32, 3 * n, off).reshape(3, hdr[3], hdr[2], hdr[1])
         off += 12 * n
-        S = md.sub
+        S = md.sub_size
         exp = md.ranks[r]["solver"].velocity.reshape(3, S[2], S[1], S[0])[:, 1:-1, 1:-1, 1:-1]
         assert hdr[0] == r and bits_equal(vel, exp), r
 
