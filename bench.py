@@ -42,62 +42,89 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons DURING the timed region.  NVML is polled from a thread every
+    few ms (the timed region of the default run is < 0.1 s, too short for `nvidia-smi -lms`);
+    falls back to one nvidia-smi query if the NVML binding is unavailable."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.lines = []
-        self.mark_at = 0
-        self.proc = None
+        self.samples = []          # (t, sm_mhz, reasons_bitmask, power_w)
+        self.mark_t = None
+        self.stop_flag = False
+        self.thread = None
+        self.sm_max = None
+        self.backend = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.backend = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.backend = "nvidia-smi"
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((time.perf_counter(), sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def mark(self):
-        """start of the timed region: earlier samples (warm-up) are reported separately"""
-        self.mark_at = len(self.lines)
+        """start of the timed region (samples before it belong to the warm-up)"""
+        self.mark_t = time.perf_counter()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        time.sleep(0.15)
-        self.proc.terminate()
+        end_t = time.perf_counter()
+        self.stop_flag = True
+        if self.backend == "nvml":
+            self.thread.join(timeout=1.0)
+            timed = [x for x in self.samples if self.mark_t is None or self.mark_t <= x[0] <= end_t]
+            use = timed if len(timed) >= 3 else self.samples
+            reasons = set()
+            for _, _, rs, _ in use:
+                for name, bit in self.BAD.items():
+                    if rs & bit:
+                        reasons.add(name)
+            pw = [x[3] for x in use if x[3] is not None]
+            return {"sm_mhz": float(np.median([x[1] for x in use])) if use else None, "sm_max_mhz": self.sm_max,
+                    "samples": len(use), "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons),
+                    "source": "nvml polled every 4 ms during the timed region"}
         try:
-            self.proc.wait(timeout=2)
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            reasons = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6])
+                       if v.strip().lower().startswith("active")]
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "samples": 1, "reasons": reasons,
+                    "source": "nvidia-smi after the timed region"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        timed = self.lines[self.mark_at:]
-        # a short timed region may see only a couple of 100 ms samples: fall back to every
-        # sample taken under load since the warm-up started
-        for ln in (timed if len(timed) >= 3 else self.lines):
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": []}
 
 
 def decomposition(n_gpus, decomp):
@@ -308,12 +335,25 @@ def run_gpu(args):
             s.simulationStep()
         ms_nc = max_over_ranks(s.timerStop())
         barrier()
+        timeline = None
+        if args.sync == "p2p":
+            # device timestamps of single overlapped steps: fork -> shell done / interior done /
+            # exchange done / join (mean over 10 beta and 10 alpha steps, max over ranks)
+            acc = np.zeros((2, 4))
+            for i in range(20):
+                acc[i & 1] += np.array(s.commStepTimed())
+            acc /= 10.0
+            timeline = {}
+            for k, name in enumerate(("beta_step", "alpha_step")):
+                v = [max_over_ranks(float(x)) for x in acc[k]]
+                timeline[name] = {"shell_done": v[0], "interior_done": v[1], "exchange_done": v[2], "join": v[3]}
+            barrier()
         face_bytes = 0
         for c in ctrl.getComms():
             face_bytes += 5 * int(np.prod(c.getSendSize())) * elem
         halo = {"ms_per_step_no_exchange": ms_nc / K, "ms_per_step": ms / K,
                 "exposed_frac": max(0.0, 1.0 - ms_nc / ms), "hidden_frac": min(1.0, ms_nc / ms),
-                "bytes_sent_per_step_per_gpu": face_bytes,
+                "bytes_sent_per_step_per_gpu": face_bytes, "timeline_ms": timeline,
                 "note": "exposed = 1 - t_step(step kernels only) / t_step(with halo exchange), max over ranks"}
 
     # ---- per-kernel timing (alpha / beta alone), single GPU only: explains the roofline

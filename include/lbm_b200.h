@@ -174,6 +174,10 @@ int lbmCommSync(lbm_t h, int sync_kind);                /* begin; for axis x,y,z
 /* one overlapped time step: shell kernels -> (push/pull on the comm stream || interior kernel)
  * -> join; == CController::computeNextStep (src/CController.hpp:385-391) */
 int lbmCommStep(lbm_t h);
+/* the same step with CUDA events on both streams; ms = time from the fork to {shell kernels done,
+ * interior kernel done, exchange (push/wait/unpack) done, join}: shows how much of the halo
+ * exchange is hidden under the interior kernel.  Synchronises. */
+int lbmCommStepTimed(lbm_t h, float ms[4]);
 
 /* ---- overlap support: the step split into the shell next to ghost faces and the interior.
  *      ghost_faces: bit a*2+s set = face (axis a, side s) has a neighbour. --------------- */

@@ -88,6 +88,7 @@ SYMBOLS = {
     "lbmCommStep": (_i, [_vp]),
     "lbmStepShell": (_i, [_vp, _i]),
     "lbmStepShellComm": (_i, [_vp, _i]),
+    "lbmCommStepTimed": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "lbmGetSlotStride": (_i, [_vp, ctypes.POINTER(ctypes.c_size_t)]),
     "lbmStepInterior": (_i, [_vp, _i]),
     "lbmStreamWaitStream": (_i, [_vp, _i]),

@@ -53,7 +53,7 @@ struct lbm_solver {
 	cudaStream_t compute, comm;
 	cudaStream_t step_aux;       /* non-NULL while the comm stream is forked off the compute stream */
 	bool own_compute, own_comm;
-	cudaEvent_t ev_compute, ev_comm, ev_t0, ev_t1;
+	cudaEvent_t ev_compute, ev_comm, ev_t0, ev_t1, ev_h2d;
 	uint64_t counter;
 	uint64_t launches;
 	int vec;
@@ -329,6 +329,7 @@ int set_field(lbm_t h, void *field, size_t elem, int comps, const void *host_src
 	const size_t bytes = (size_t)comps * size[0] * size[1] * size[2] * elem;
 	if (int rc = ensure_staging(h, bytes)) return rc;
 	CUDA_TRY(h, cudaMemcpyAsync(h->staging, host_src, bytes, cudaMemcpyHostToDevice, h->compute));
+	CUDA_TRY(h, cudaEventRecord(h->ev_h2d, h->compute));
 	int ids[19], nsel = 0;
 	for (int c = 0; c < comps; c++) if (!keep || keep[c]) ids[nsel++] = c;
 	if (nsel > 0) {
@@ -336,8 +337,9 @@ int set_field(lbm_t h, void *field, size_t elem, int comps, const void *host_src
 		launch_rect_bytes(h, elem, h->staging, field, R, h->compute);
 		CUDA_TRY(h, cudaGetLastError());
 	}
-	/* the host buffer is consumed before return (CL_MEM_COPY_HOST_PTR semantics) */
-	CUDA_TRY(h, cudaStreamSynchronize(h->compute));
+	/* the host buffer is consumed before return (CL_MEM_COPY_HOST_PTR semantics): wait for the
+	 * upload only -- the scatter kernel stays queued ahead of whatever the caller launches next */
+	CUDA_TRY(h, cudaEventSynchronize(h->ev_h2d));
 	return LBM_OK;
 }
 
@@ -432,6 +434,7 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	}
 	CREATE_TRY(cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+	CREATE_TRY(cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming));
 	CREATE_TRY(cudaEventCreate(&h->ev_t0));
 	CREATE_TRY(cudaEventCreate(&h->ev_t1));
 	CREATE_TRY(cudaMalloc(&h->dd, (size_t)19 * h->stride * h->elem));
@@ -462,6 +465,7 @@ int lbmDestroy(lbm_t h)
 	cudaFree(h->staging); cudaFree(h->d_checksum);
 	if (h->ev_compute) cudaEventDestroy(h->ev_compute);
 	if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+	if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
 	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
 	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
 	if (h->own_compute && h->compute) cudaStreamDestroy(h->compute);
@@ -1010,25 +1014,54 @@ int lbmCommSync(lbm_t h, int sync_kind)
 	return LBM_OK;
 }
 
-int lbmCommStep(lbm_t h)
+static int comm_step(lbm_t h, cudaEvent_t *marks /* NULL or 5 timing events */)
 {
-	CHECK_HANDLE(h);
 	if (int rc = use_device(h)) return rc;
-	if (h->faces.empty()) return lbmStep(h);
 	const int faces = ghost_mask_of_faces(h);
 	const int kind = (h->counter & 1) ? LBM_SYNC_ALPHA : LBM_SYNC_BETA;   /* the sync that follows this step */
 	/* fork: the (high-priority) comm stream runs shell -> push -> wait -> unpack while the
 	 * compute stream runs the interior kernel; shell and interior touch disjoint
 	 * (slot, location) pairs (A-A invariant), so they may run concurrently.  The shell is
 	 * enqueued first so that its few blocks are scheduled ahead of the interior's. */
+	if (marks) CUDA_TRY(h, cudaEventRecord(marks[0], h->compute));
 	if (int rc = lbmStreamWaitStream(h, 1)) return rc;
 	if (int rc = lbmStepShellComm(h, faces)) return rc;
+	if (marks) CUDA_TRY(h, cudaEventRecord(marks[1], h->comm));
 	h->step_aux = h->comm;                                  /* the comm stream is forked: wrapping kernel there */
 	int rc_int = lbmStepInterior(h, faces);
 	h->step_aux = NULL;
 	if (rc_int) return rc_int;
+	if (marks) CUDA_TRY(h, cudaEventRecord(marks[2], h->compute));
 	if (int rc = lbmCommSync(h, kind)) return rc;
-	return lbmStreamWaitStream(h, 0);                       /* join: the next step needs the halo */
+	if (marks) CUDA_TRY(h, cudaEventRecord(marks[3], h->comm));
+	if (int rc = lbmStreamWaitStream(h, 0)) return rc;     /* join: the next step needs the halo */
+	if (marks) CUDA_TRY(h, cudaEventRecord(marks[4], h->compute));
+	return LBM_OK;
+}
+
+int lbmCommStep(lbm_t h)
+{
+	CHECK_HANDLE(h);
+	if (h->faces.empty()) return lbmStep(h);
+	return comm_step(h, NULL);
+}
+
+int lbmCommStepTimed(lbm_t h, float ms[4])
+{
+	CHECK_HANDLE(h);
+	if (!ms) return fail(h, LBM_ERR_INVALID, "null ms");
+	if (h->faces.empty()) return fail(h, LBM_ERR_INVALID, "no halo faces registered");
+	if (int rc = use_device(h)) return rc;
+	cudaEvent_t ev[5];
+	for (int i = 0; i < 5; i++) CUDA_TRY(h, cudaEventCreate(&ev[i]));
+	int rc = comm_step(h, ev);
+	if (rc == LBM_OK) {
+		cudaError_t e = cudaEventSynchronize(ev[4]);
+		for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventElapsedTime(&ms[i], ev[0], ev[i + 1]);
+		if (e != cudaSuccess) rc = fail(h, LBM_ERR_CUDA, cudaGetErrorString(e));
+	}
+	for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]);
+	return rc;
 }
 
 int lbmGetDevicePointer(lbm_t h, int which, void **ptr, size_t *bytes)

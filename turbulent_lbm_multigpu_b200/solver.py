@@ -275,6 +275,13 @@ class CLbmSolver:
     def stepShell(self, ghost_faces):
         self._ck(self._lib.lbmStepShell(self._h, int(ghost_faces)))
 
+    def commStepTimed(self):
+        """one overlapped step with device timestamps: ms from the fork to (shell done, interior done,
+        exchange done, join)"""
+        ms = (ctypes.c_float * 4)()
+        self._ck(self._lib.lbmCommStepTimed(self._h, ms))
+        return tuple(float(v) for v in ms)
+
     def stepShellComm(self, ghost_faces):
         """shell kernels on the comm stream: they run next to the interior kernel"""
         self._ck(self._lib.lbmStepShellComm(self._h, int(ghost_faces)))
