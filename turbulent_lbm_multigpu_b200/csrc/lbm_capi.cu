@@ -828,7 +828,7 @@ int face_push(lbm_t h, lbm_face &f, int kind, cudaStream_t s)
 	const RectCopy R = rect_desc(h, origin, f.size, true, field, packed, n, h->stride);
 	const long long total = (long long)f.size[0] * f.size[1] * f.size[2] * n;
 	long long grid = (total + 255) / 256;
-	if (grid > 148LL * 4) grid = 148LL * 4;
+	if (grid > 148LL) grid = 148LL;
 	volatile unsigned int *flag = (volatile unsigned int *)(f.peer_block + 64 * kind);
 	char *stage = f.peer_block + f.peer_stage_off[kind];
 	if (h->dtype == LBM_F32)

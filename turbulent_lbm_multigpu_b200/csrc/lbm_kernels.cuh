@@ -714,16 +714,18 @@ __global__ void halo_push_kernel(const T *__restrict__ src, T *__restrict__ peer
 				+ (long long)(R.so[1] + j) * R.ss[0] + (long long)(R.so[2] + k) * R.ss[0] * R.ss[1];
 		peer_staging[t] = src[s];                 /* staging layout [slot][z][y][x] == linear t */
 	}
-	/* publish: every block fences its peer stores, the last one raises the flag */
-	__threadfence_system();
+	/* publish: ONE thread per block fences (system scope, cumulative over the block's peer
+	 * stores it observed through the barrier), the last block raises the flag.  A fence of
+	 * scope >= cluster invalidates the SM's L1 (CCTL.IVALL), which the step kernel running
+	 * next to this one depends on -- so no per-thread fences and a small grid. */
 	__syncthreads();
 	if (threadIdx.x == 0) {
+		__threadfence_system();
 		const unsigned int done = atomicAdd(block_counter, 1u);
 		if (done == gridDim.x - 1) {
 			*block_counter = 0;                   /* ready for the next push of this face */
 			__threadfence_system();
 			*peer_flag = seq;
-			__threadfence_system();
 		}
 	}
 }
