@@ -128,9 +128,12 @@ class ClockSampler:
 
 
 def decomposition(n_gpus, decomp):
-    """(1,1,n) z-slabs (contiguous faces), the reference's x split, or blocks."""
+    """(1,1,n) z-slabs (contiguous faces), the reference's x split, y-z pencils
+    (faces made of whole x rows: no strided x faces) or 3-D blocks."""
     if decomp == "slab-x":
         return (n_gpus, 1, 1)
+    if decomp == "pencil":
+        return {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)}[n_gpus]
     if decomp == "block":
         return {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}[n_gpus]
     return (1, 1, n_gpus)
@@ -444,7 +447,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=SIZE, help="cells per axis (per GPU for weak scaling)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--decomp", default="slab", choices=["slab", "slab-x", "block"])
+    ap.add_argument("--decomp", default="slab", choices=["slab", "slab-x", "pencil", "block"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--cs", type=float, default=CS, help="Smagorinsky constant (0 = plain BGK, the reference)")
     ap.add_argument("--sync", default="p2p", choices=["host", "device", "overlap", "p2p"],

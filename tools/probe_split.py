@@ -17,10 +17,13 @@ def main():
     size = (256, 256, 256)
     steps = 100
     p = compute_parameters(size, (0.1,) * 3, dtype=np.float32)
-    faces = 0b110000                     # ghost faces z-, z+
-    out = {}
-    for cs in (0.0, 0.1):
-        s = CLbmSolver(0, 0, [[1, 1], [1, 1], [8, 8]], CDomain(0, size, (0, 0, 0), (0.1,) * 3), dtype=np.float32,
+    axis = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    faces = 0b11 << (2 * axis)           # ghost faces on both sides of that axis
+    bc = [[1, 1], [1, 1], [1, 1]]
+    bc[axis] = [8, 8]
+    out = {"axis": axis}
+    for cs in (0.1,):
+        s = CLbmSolver(0, 0, bc, CDomain(0, size, (0, 0, 0), (0.1,) * 3), dtype=np.float32,
                        store_velocity=False, store_density=False, smagorinsky_cs=cs, params=p)
 
         def unsplit():
@@ -35,8 +38,11 @@ def main():
         def interior_only():
             s.stepInterior(faces)
 
+        def shell_only():
+            s.stepShell(faces)
+
         for name, fn in (("unsplit", unsplit), ("split_concurrent", split_concurrent), ("split_serial", split_serial),
-                         ("interior_only", interior_only)):
+                         ("interior_only", interior_only), ("shell_only", shell_only)):
             for _ in range(6):
                 fn()
             s.wait()

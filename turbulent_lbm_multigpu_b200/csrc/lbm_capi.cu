@@ -20,7 +20,9 @@ namespace {
 
 thread_local std::string g_last_error;
 
-struct Box { int x0, nx, y0, ny, z0, nz; };
+/* iteration box; zb/nzb: optional second z range [zb, zb+nzb) above the first, same x/y extent,
+ * updated by the SAME launch (the two z shells of a slab) */
+struct Box { int x0, nx, y0, ny, z0, nz, zb, nzb; };
 
 } // namespace
 
@@ -51,6 +53,7 @@ struct lbm_solver {
 	void *staging; size_t staging_bytes;
 	double *d_checksum;
 	cudaStream_t compute, comm;
+	int xshell;                  /* width (cells) of the shell next to an x ghost face */
 	cudaStream_t step_aux;       /* non-NULL while the comm stream is forked off the compute stream */
 	bool own_compute, own_comm;
 	cudaEvent_t ev_compute, ev_comm, ev_t0, ev_t1, ev_h2d;
@@ -96,8 +99,9 @@ StepParams<T> make_params(lbm_t h, const Box &b)
 	P.smag_k = (T)(18.0 * std::sqrt(2.0) * h->desc.smagorinsky_cs * h->desc.smagorinsky_cs);
 	P.gx = (T)h->desc.gravitation[0]; P.gy = (T)h->desc.gravitation[1]; P.gz = (T)h->desc.gravitation[2];
 	P.u_lid = (T)h->u_lid;
-	P.x0 = b.x0; P.nx = b.nx; P.y0 = b.y0; P.ny = b.ny; P.z0 = b.z0; P.nz = b.nz;
-	P.zsplit = 0x7fffffff; P.zjump = 0;
+	P.x0 = b.x0; P.nx = b.nx; P.y0 = b.y0; P.ny = b.ny; P.z0 = b.z0; P.nz = b.nz + b.nzb;
+	if (b.nzb > 0) { P.zsplit = b.nz; P.zjump = b.zb - (b.z0 + b.nz); }
+	else { P.zsplit = 0x7fffffff; P.zjump = 0; }
 	P.wg = h->wg_quirk;
 	P.store_v = h->desc.store_velocity; P.store_r = h->desc.store_density;
 	return P;
@@ -117,16 +121,22 @@ void launch_beta(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStr
 	/* general kernel: only z planes whose blocks can reach across the array ends
 	 * (|delta| <= sxy + sx + 1 -> planes 0,1 and sz-2,sz-1), or everything with the quirk */
 	const int zlo_end = P.wg > 0 ? P.sz : 2, zhi_begin = P.wg > 0 ? P.sz : P.sz - 2;
-	int ranges[2][2] = { { P.z0, (P.z0 + P.nz < zlo_end ? P.z0 + P.nz : zlo_end) },
-	                     { (P.z0 > zhi_begin ? P.z0 : zhi_begin), P.z0 + P.nz } };
-	if (ranges[1][0] < ranges[0][1]) ranges[1][0] = ranges[0][1];
+	/* the box is one z range [a0,a1) or two ([a0,a1) below [b0,b1)): the low general planes can
+	 * only lie in the first piece, the high ones only in the last */
+	const bool two = P.zsplit < P.nz;
+	const int a0 = P.z0, a1 = P.z0 + (two ? P.zsplit : P.nz);
+	const int b0 = two ? a1 + P.zjump : a0, b1 = two ? P.z0 + P.nz + P.zjump : a1;
+	int ranges[2][2] = { { a0, (a1 < zlo_end ? a1 : zlo_end) },
+	                     { (b0 > zhi_begin ? b0 : zhi_begin), b1 } };
+	if (P.wg > 0 && two) { ranges[0][1] = a1; ranges[1][0] = b0; }     /* quirk: every plane is general */
+	if (!two && ranges[1][0] < ranges[0][1]) ranges[1][0] = ranges[0][1];
 	/* both z ranges in ONE launch: grid rows [0, nlo) -> low planes, [nlo, nlo+nhi) -> high planes */
 	const int nlo = ranges[0][1] > ranges[0][0] ? ranges[0][1] - ranges[0][0] : 0;
 	const int nhi = ranges[1][1] > ranges[1][0] ? ranges[1][1] - ranges[1][0] : 0;
 	if (nlo + nhi > 0) {
 		StepParams<T> Q = P;
 		if (nlo > 0) { Q.z0 = ranges[0][0]; Q.zsplit = nlo; Q.zjump = ranges[1][0] - (ranges[0][0] + nlo); }
-		else { Q.z0 = ranges[1][0]; }
+		else { Q.z0 = ranges[1][0]; Q.zsplit = 0x7fffffff; Q.zjump = 0; }
 		Q.nz = nlo + nhi;
 		dim3 g2(grid.x, (unsigned)Q.nz);
 		if (shipped) lbm_beta_general_kernel<T, VEC, SMAG, STORE, 0><<<g2, block, 0, sg>>>(Q);
@@ -145,11 +155,11 @@ void launch_beta(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStr
 template <typename T, int VEC>
 int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream_t sg)
 {
-	if (b.nx <= 0 || b.ny <= 0 || b.nz <= 0) return LBM_OK;
+	if (b.nx <= 0 || b.ny <= 0 || b.nz + b.nzb <= 0) return LBM_OK;
 	const StepParams<T> P = make_params<T>(h, b);
 	const long long groups = ((long long)b.nx * b.ny) / VEC;
 	dim3 block(h->block);
-	dim3 grid((unsigned)((groups + h->block - 1) / h->block), (unsigned)b.nz);
+	dim3 grid((unsigned)((groups + h->block - 1) / h->block), (unsigned)(b.nz + b.nzb));
 	const bool store = h->desc.store_velocity || h->desc.store_density;
 #define LBM_DISPATCH(FN)                                              \
 	do {                                                              \
@@ -182,7 +192,7 @@ int launch_step(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream_t 
 	}
 }
 
-Box full_box(lbm_t h) { Box b = { 0, h->sx, 0, h->sy, 0, h->sz }; return b; }
+Box full_box(lbm_t h) { Box b = { 0, h->sx, 0, h->sy, 0, h->sz, 0, 0 }; return b; }
 
 /*
  * Partition of the sub-domain for communication/computation overlap: the shell is every
@@ -196,24 +206,28 @@ void partition(lbm_t h, int ghost_faces, std::vector<Box> &shell, Box &interior)
 	int lo[3], hi[3];
 	for (int a = 0; a < 3; a++) {
 		int t = 2;
-		if (a == 0) { t = 32; while (t > 2 && (t > S[0] / 4 || (S[0] % t) != 0)) t >>= 1; if (t < h->vec) t = h->vec; }
+		if (a == 0) { t = h->xshell; while (t > 2 && (t > S[0] / 4 || (S[0] % t) != 0)) t >>= 1; if (t < h->vec) t = h->vec; if (t < 2) t = 2; }
 		lo[a] = (ghost_faces >> (2 * a)) & 1 ? t : 0;
 		hi[a] = (ghost_faces >> (2 * a + 1)) & 1 ? S[a] - t : S[a];
 		if (lo[a] > hi[a]) { lo[a] = 0; hi[a] = 0; }   /* everything is shell */
 	}
 	shell.clear();
 	/* z shells: full x,y */
-	if (lo[2] > 0) shell.push_back(Box{ 0, S[0], 0, S[1], 0, lo[2] });
-	if (hi[2] < S[2]) shell.push_back(Box{ 0, S[0], 0, S[1], hi[2], S[2] - hi[2] });
+	if (lo[2] > 0 && hi[2] < S[2] && hi[2] > lo[2])      /* both z shells: one launch */
+		shell.push_back(Box{ 0, S[0], 0, S[1], 0, lo[2], hi[2], S[2] - hi[2] });
+	else {
+		if (lo[2] > 0) shell.push_back(Box{ 0, S[0], 0, S[1], 0, lo[2], 0, 0 });
+		if (hi[2] < S[2]) shell.push_back(Box{ 0, S[0], 0, S[1], hi[2], S[2] - hi[2], 0, 0 });
+	}
 	const int z0 = lo[2], nz = hi[2] - lo[2];
 	/* y shells: full x, interior z */
-	if (lo[1] > 0) shell.push_back(Box{ 0, S[0], 0, lo[1], z0, nz });
-	if (hi[1] < S[1]) shell.push_back(Box{ 0, S[0], hi[1], S[1] - hi[1], z0, nz });
+	if (lo[1] > 0) shell.push_back(Box{ 0, S[0], 0, lo[1], z0, nz, 0, 0 });
+	if (hi[1] < S[1]) shell.push_back(Box{ 0, S[0], hi[1], S[1] - hi[1], z0, nz, 0, 0 });
 	const int y0 = lo[1], ny = hi[1] - lo[1];
 	/* x shells: interior y,z */
-	if (lo[0] > 0) shell.push_back(Box{ 0, lo[0], y0, ny, z0, nz });
-	if (hi[0] < S[0]) shell.push_back(Box{ hi[0], S[0] - hi[0], y0, ny, z0, nz });
-	interior = Box{ lo[0], hi[0] - lo[0], y0, ny, z0, nz };
+	if (lo[0] > 0) shell.push_back(Box{ 0, lo[0], y0, ny, z0, nz, 0, 0 });
+	if (hi[0] < S[0]) shell.push_back(Box{ hi[0], S[0] - hi[0], y0, ny, z0, nz, 0, 0 });
+	interior = Box{ lo[0], hi[0] - lo[0], y0, ny, z0, nz, 0, 0 };
 }
 
 int ensure_staging(lbm_t h, size_t bytes)
@@ -403,6 +417,8 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	h->dd = h->velocity = h->density = NULL; h->flags = NULL;
 	h->staging = NULL; h->staging_bytes = 0; h->d_checksum = NULL;
 	h->counter = 0; h->launches = 0; h->step_aux = NULL;
+	h->xshell = 32;
+	if (const char *e = getenv("LBM_B200_XSHELL")) h->xshell = atoi(e) > 1 ? atoi(e) : 2;
 	h->sync_seq[0] = h->sync_seq[1] = 0;
 	h->smag = d->smagorinsky_cs != 0.0;
 	h->u_lid = d->u_lid;
@@ -818,45 +834,92 @@ int face_check(lbm_t h, int face_id)
 	return LBM_OK;
 }
 
-int face_push(lbm_t h, lbm_face &f, int kind, cudaStream_t s)
+/* widest vector (in elements, <= 16 B) that every row of the face can be moved with */
+int face_vec(lbm_t h, const int origin[3], const int size[3])
 {
-	if (!f.connected) return fail(h, LBM_ERR_INVALID, "halo face is not connected to its peer");
-	const int *origin = kind == LBM_SYNC_BETA ? f.recv_origin : f.send_origin;
-	int field[19], packed[19], n = 0;
-	for (int k = 0; k < 19; k++) if ((f.send_mask[kind] >> k) & 1) { field[n] = k; packed[n] = n; n++; }
-	if (n == 0) return LBM_OK;
-	const RectCopy R = rect_desc(h, origin, f.size, true, field, packed, n, h->stride);
-	const long long total = (long long)f.size[0] * f.size[1] * f.size[2] * n;
-	long long grid = (total + 255) / 256;
-	if (grid > 148LL) grid = 148LL;
-	volatile unsigned int *flag = (volatile unsigned int *)(f.peer_block + 64 * kind);
-	char *stage = f.peer_block + f.peer_stage_off[kind];
-	if (h->dtype == LBM_F32)
-		halo_push_kernel<float><<<(unsigned)grid, 256, 0, s>>>((const float *)h->dd, (float *)stage, R,
-				f.block_counter, flag, h->sync_seq[kind]);
-	else
-		halo_push_kernel<double><<<(unsigned)grid, 256, 0, s>>>((const double *)h->dd, (double *)stage, R,
-				f.block_counter, flag, h->sync_seq[kind]);
+	int v = (int)(16 / h->elem);
+	while (v > 1 && ((size[0] % v) || (origin[0] % v) || (h->sx % v) || (h->stride % v))) v >>= 1;
+	return v;
+}
+
+void fill_face(lbm_t h, HaloFace &F, const int origin[3], const int size[3])
+{
+	F.dd = h->dd; F.dd_stride = h->stride;
+	for (int a = 0; a < 3; a++) { F.origin[a] = origin[a]; F.size[a] = size[a]; }
+	F.ss[0] = h->sx; F.ss[1] = h->sy;
+	F.vec = face_vec(h, origin, size);
+}
+
+unsigned face_blocks(const HaloFace &F)
+{
+	const long long work = ((long long)F.size[0] * F.size[1] * F.size[2] * F.ncomp) / F.vec;
+	long long g = (work + 255) / 256;
+	if (g > 148) g = 148;               /* few blocks: every block ends with a system fence (push) or spins (pull) */
+	return (unsigned)(g < 1 ? 1 : g);
+}
+
+/* every face of one axis in ONE launch on the comm stream */
+int axis_push(lbm_t h, int kind, int axis, cudaStream_t s)
+{
+	HaloAxis A;
+	memset(&A, 0, sizeof(A));
+	unsigned nf = 0, blocks = 1;
+	for (size_t i = 0; i < h->faces.size(); i++) {
+		lbm_face &f = h->faces[i];
+		if (f.axis != axis) continue;
+		if (!f.connected) return fail(h, LBM_ERR_INVALID, "halo face is not connected to its peer");
+		if (nf == 2) return fail(h, LBM_ERR_INVALID, "more than two halo faces on one axis");
+		HaloFace &F = A.f[nf];
+		fill_face(h, F, kind == LBM_SYNC_BETA ? f.recv_origin : f.send_origin, f.size);
+		int n = 0;
+		for (int k = 0; k < 19; k++) if ((f.send_mask[kind] >> k) & 1) { F.dd_comp[n] = k; F.st_comp[n] = n; n++; }
+		F.ncomp = n;
+		F.staging = f.peer_block + f.peer_stage_off[kind];
+		F.flag = (volatile unsigned int *)(f.peer_block + 64 * kind);
+		F.block_counter = f.block_counter;
+		const unsigned b = face_blocks(F);
+		if (b > blocks) blocks = b;
+		nf++;
+	}
+	if (nf == 0) return LBM_OK;
+	dim3 grid(blocks, nf);
+	if (h->dtype == LBM_F32) halo_push_kernel<float><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
+	else halo_push_kernel<double><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
 	h->launches++;
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
 }
 
-int face_pull(lbm_t h, lbm_face &f, int kind, cudaStream_t s)
+int axis_pull(lbm_t h, int kind, int axis, cudaStream_t s)
 {
-	const int *origin = kind == LBM_SYNC_BETA ? f.send_origin : f.recv_origin;
-	int field[19], packed[19], n = 0, pos = 0;
-	for (int k = 0; k < 19; k++) {
-		if (!((f.recv_mask[kind] >> k) & 1)) continue;
-		if ((f.write_mask[kind] >> k) & 1) { field[n] = k; packed[n] = pos; n++; }
-		pos++;
+	HaloAxis A;
+	memset(&A, 0, sizeof(A));
+	unsigned nf = 0, blocks = 1;
+	for (size_t i = 0; i < h->faces.size(); i++) {
+		lbm_face &f = h->faces[i];
+		if (f.axis != axis) continue;
+		if (nf == 2) return fail(h, LBM_ERR_INVALID, "more than two halo faces on one axis");
+		HaloFace &F = A.f[nf];
+		fill_face(h, F, kind == LBM_SYNC_BETA ? f.send_origin : f.recv_origin, f.size);
+		int n = 0, pos = 0;
+		for (int k = 0; k < 19; k++) {
+			if (!((f.recv_mask[kind] >> k) & 1)) continue;
+			if ((f.write_mask[kind] >> k) & 1) { F.dd_comp[n] = k; F.st_comp[n] = pos; n++; }
+			pos++;
+		}
+		F.ncomp = n;
+		F.staging = f.local_block + f.stage_off[kind];
+		F.flag = (volatile unsigned int *)(f.local_block + 64 * kind);
+		F.block_counter = NULL;
+		const unsigned b = face_blocks(F);
+		if (b > blocks) blocks = b;
+		nf++;
 	}
-	halo_wait_kernel<<<1, 1, 0, s>>>((volatile unsigned int *)(f.local_block + 64 * kind), h->sync_seq[kind]);
+	if (nf == 0) return LBM_OK;
+	dim3 grid(blocks, nf);
+	if (h->dtype == LBM_F32) halo_pull_kernel<float><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
+	else halo_pull_kernel<double><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
 	h->launches++;
-	if (n > 0) {
-		const RectCopy R = rect_desc(h, origin, f.size, false, field, packed, n, h->stride);
-		launch_rect_bytes(h, h->elem, f.local_block + f.stage_off[kind], h->dd, R, s);
-	}
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
 }
@@ -985,20 +1048,14 @@ int lbmCommPush(lbm_t h, int sync_kind, int axis)
 {
 	CHECK_HANDLE(h);
 	if (int rc = use_device(h)) return rc;
-	for (size_t i = 0; i < h->faces.size(); i++)
-		if (h->faces[i].axis == axis)
-			if (int rc = face_push(h, h->faces[i], sync_kind, h->comm)) return rc;
-	return LBM_OK;
+	return axis_push(h, sync_kind, axis, h->comm);
 }
 
 int lbmCommPull(lbm_t h, int sync_kind, int axis)
 {
 	CHECK_HANDLE(h);
 	if (int rc = use_device(h)) return rc;
-	for (size_t i = 0; i < h->faces.size(); i++)
-		if (h->faces[i].axis == axis)
-			if (int rc = face_pull(h, h->faces[i], sync_kind, h->comm)) return rc;
-	return LBM_OK;
+	return axis_pull(h, sync_kind, axis, h->comm);
 }
 
 int lbmCommSync(lbm_t h, int sync_kind)

@@ -688,51 +688,113 @@ __global__ void rect_copy_kernel(const T *__restrict__ src, T *__restrict__ dst,
 
 /* ================================================================== peer-memory halo
  * One-sided halo exchange over NVLink peer memory (same process or CUDA-IPC mapped):
- *   halo_push_kernel  packs the selected slots of a dd rect and stores them STRAIGHT INTO the
- *                     neighbour's staging buffer (peer stores: pack + send fused); the last
- *                     block to finish publishes a sequence number in the neighbour's flag word;
- *   halo_wait_kernel  one thread spins (acquire, system scope) until the local flag reaches the
- *                     expected sequence number;
- *   rect_copy_kernel  then unpacks the local staging buffer into the dd rect.
+ *   halo_push_kernel  packs the selected slots of the (up to two) faces of one axis and stores
+ *                     them STRAIGHT INTO the neighbours' staging buffers (peer stores: pack +
+ *                     send fused); the last block of a face publishes a sequence number in the
+ *                     neighbour's flag word;
+ *   halo_pull_kernel  waits (acquire, system scope) until the local flags reach the expected
+ *                     sequence number and unpacks the local staging buffers into the dd rects.
  * Replaces storeDensityDistribution -> MPI_Isend/Irecv/Waitall -> setDensityDistribution
  * (reference src/CController.hpp:265-383). */
+/* One halo face of a fused launch.  dd side: [slot][z][y][x] rect inside the sub-domain with
+ * slot stride dd_stride; staging side: dense [selected slot][z][y][x].  vec = elements moved
+ * per thread and step (4/2 when rows are whole, aligned multiples -- y and z faces; 1 for x faces). */
+struct HaloFace {
+	void *dd;                       /* sub-domain populations (local) */
+	void *staging;                  /* push: the NEIGHBOUR's receive block (peer memory); pull: mine */
+	unsigned int *block_counter;    /* push only */
+	volatile unsigned int *flag;    /* push: the neighbour's flag word; pull: mine */
+	long long dd_stride;
+	int origin[3], size[3];         /* rect in the sub-domain */
+	int ss[2];                      /* sub-domain Sx, Sy */
+	int ncomp;
+	int dd_comp[19];                /* slot on the dd side   */
+	int st_comp[19];                /* position on the staging side */
+	int vec;
+};
+struct HaloAxis { HaloFace f[2]; };
+
+/* element e (in units of vec) of a face -> offsets on both sides; 32-bit arithmetic */
 template <typename T>
-__global__ void halo_push_kernel(const T *__restrict__ src, T *__restrict__ peer_staging, const RectCopy R,
-		unsigned int *block_counter, volatile unsigned int *peer_flag, unsigned int seq)
+__device__ __forceinline__ void halo_offsets(const HaloFace &F, unsigned int e, long long &dd_off, long long &st_off)
 {
-	const long long cells = (long long)R.block[0] * R.block[1] * R.block[2];
-	const long long total = cells * R.ncomp;
-	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-			t += (long long)gridDim.x * blockDim.x) {
-		const int c = (int)(t / cells);
-		long long r = t - (long long)c * cells;
-		const int k = (int)(r / ((long long)R.block[0] * R.block[1]));
-		r -= (long long)k * R.block[0] * R.block[1];
-		const int j = (int)(r / R.block[0]);
-		const int i = (int)(r - (long long)j * R.block[0]);
-		const long long s = (long long)R.src_comp[c] * R.src_comp_stride + (R.so[0] + i)
-				+ (long long)(R.so[1] + j) * R.ss[0] + (long long)(R.so[2] + k) * R.ss[0] * R.ss[1];
-		peer_staging[t] = src[s];                 /* staging layout [slot][z][y][x] == linear t */
+	const unsigned int xw = (unsigned int)F.size[0] / (unsigned int)F.vec;
+	const unsigned int i = e % xw; unsigned int r = e / xw;
+	const unsigned int j = r % (unsigned int)F.size[1]; r /= (unsigned int)F.size[1];
+	const unsigned int k = r % (unsigned int)F.size[2];
+	const unsigned int c = r / (unsigned int)F.size[2];
+	const long long cells = (long long)F.size[0] * F.size[1] * F.size[2];
+	dd_off = (long long)F.dd_comp[c] * F.dd_stride + (F.origin[0] + (long long)i * F.vec)
+			+ (long long)(F.origin[1] + j) * F.ss[0] + (long long)(F.origin[2] + k) * F.ss[0] * F.ss[1];
+	st_off = (long long)F.st_comp[c] * cells + ((long long)k * F.size[1] + j) * F.size[0] + (long long)i * F.vec;
+}
+
+template <typename T, int VEC> struct HaloVec;
+template <> struct HaloVec<float, 4> { typedef float4 type; };
+template <> struct HaloVec<float, 2> { typedef float2 type; };
+template <> struct HaloVec<float, 1> { typedef float type; };
+template <> struct HaloVec<double, 2> { typedef double2 type; };
+template <> struct HaloVec<double, 1> { typedef double type; };
+template <> struct HaloVec<double, 4> { typedef double2 type; };   /* unused */
+
+template <typename T, int VEC>
+__device__ __forceinline__ void halo_copy(const HaloFace &F, bool to_staging)
+{
+	typedef typename HaloVec<T, VEC>::type V;
+	const unsigned int total = (unsigned int)(((long long)F.size[0] * F.size[1] * F.size[2] * F.ncomp) / VEC);
+	T *dd = (T *)F.dd, *st = (T *)F.staging;
+	for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+		long long a, b;
+		halo_offsets<T>(F, e, a, b);
+		if (to_staging) *reinterpret_cast<V *>(st + b) = *reinterpret_cast<const V *>(dd + a);
+		else *reinterpret_cast<V *>(dd + a) = __ldcg(reinterpret_cast<const V *>(st + b));   /* L2: never a stale L1 line */
 	}
-	/* publish: ONE thread per block fences (system scope, cumulative over the block's peer
-	 * stores it observed through the barrier), the last block raises the flag.  A fence of
-	 * scope >= cluster invalidates the SM's L1 (CCTL.IVALL), which the step kernel running
-	 * next to this one depends on -- so no per-thread fences and a small grid. */
+}
+
+/* push: both faces of one axis in ONE launch (blockIdx.y = face).  Packs the face and stores it
+ * straight into the neighbour's receive block over NVLink; the last block of a face raises the
+ * neighbour's flag.  ONE thread per block fences (system scope, cumulative over the block's peer
+ * stores it observed through the barrier): a fence of scope >= cluster invalidates the SM's L1
+ * (CCTL.IVALL), which the step kernel running next to this one depends on. */
+template <typename T>
+__global__ void halo_push_kernel(const HaloAxis A, unsigned int seq)
+{
+	const HaloFace &F = A.f[blockIdx.y];
+	if (F.vec == 4) halo_copy<T, sizeof(T) == 4 ? 4 : 2>(F, true);
+	else if (F.vec == 2) halo_copy<T, 2>(F, true);
+	else halo_copy<T, 1>(F, true);
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		__threadfence_system();
-		const unsigned int done = atomicAdd(block_counter, 1u);
+		const unsigned int done = atomicAdd(F.block_counter, 1u);
 		if (done == gridDim.x - 1) {
-			*block_counter = 0;                   /* ready for the next push of this face */
+			*F.block_counter = 0;                 /* ready for the next push of this face */
 			__threadfence_system();
-			*peer_flag = seq;
+			*F.flag = seq;
 		}
 	}
 }
 
+/* pull: both faces of one axis in ONE launch.  Every block waits (one thread spins, acquire at
+ * system scope) until the neighbour's push has raised my flag, then unpacks my receive block. */
+template <typename T>
+__global__ void halo_pull_kernel(const HaloAxis A, unsigned int seq)
+{
+	const HaloFace &F = A.f[blockIdx.y];
+	if (threadIdx.x == 0) {
+		/* sequence numbers only grow; signed distance tolerates wrap-around */
+		while ((int)(*F.flag - seq) < 0) { __nanosleep(32); }
+		__threadfence_system();
+	}
+	__syncthreads();
+	if (F.vec == 4) halo_copy<T, sizeof(T) == 4 ? 4 : 2>(F, false);
+	else if (F.vec == 2) halo_copy<T, 2>(F, false);
+	else halo_copy<T, 1>(F, false);
+}
+
+/* standalone wait, for transports that unpack with lbmHaloUnpack */
 __global__ void halo_wait_kernel(volatile unsigned int *flag, unsigned int seq)
 {
-	/* sequence numbers only grow; signed distance tolerates wrap-around */
 	while ((int)(*flag - seq) < 0) { __nanosleep(64); }
 	__threadfence_system();
 }
