@@ -1,0 +1,47 @@
+"""tools/benchmark.py: the recipes generate the reference's command lines (benchmark.py:61-129)
+and the .ini averaging reads what CController::run appends (src/CController.hpp:445-477)."""
+import importlib.util
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("lbm_benchmark", os.path.join(ROOT, "tools", "benchmark.py"))
+bm = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(bm)
+
+
+def _args(argv):
+    return dict(zip(argv[1::2], argv[2::2]))
+
+
+def test_reference_recipes():
+    n, argv = bm.point("weak-1d", 4, reference_recipe=True)
+    a = _args(argv)
+    assert n == 4 and (a["-x"], a["-y"], a["-z"], a["-X"], a["-Y"], a["-Z"]) == ("4096", "1024", "32", "4", "1", "1")
+    assert float(a["-n"]) == 0.4 and float(a["-m"]) == 0.1
+    n, argv = bm.point("strong-1d", 3, reference_recipe=True)
+    a = _args(argv)
+    assert n == 8 and (a["-x"], a["-y"], a["-X"]) == ("1024", "1024", "8") and float(a["-n"]) == 0.1
+    n, argv = bm.point("weak-2d", 2, reference_recipe=True, grid=1024)
+    a = _args(argv)
+    assert n == 4 and (a["-x"], a["-y"], a["-X"], a["-Y"]) == ("2048", "2048", "2", "2")
+
+
+def test_z_slab_recipes():
+    n, argv = bm.point("weak-1d", 8, axis="z", grid=256)
+    a = _args(argv)
+    assert n == 8 and (a["-x"], a["-y"], a["-z"], a["-Z"]) == ("256", "256", "2048", "8") and abs(float(a["-p"]) - 0.8) < 1e-12
+    n, argv = bm.point("strong-2d", 2, axis="z", grid=512)
+    a = _args(argv)
+    assert n == 4 and (a["-Y"], a["-Z"], a["-X"]) == ("2", "2", "1")
+
+
+def test_ini_averaging(tmp_path):
+    for nproc, mlups in ((1, (100.0, 110.0)), (2, (200.0, 190.0))):
+        with open(tmp_path / ("benchmark_%d.ini" % nproc), "w") as f:
+            for i, m in enumerate(mlups, 1):
+                f.write("[EXP%d]\nNP : %d\nCUBE_X : 64\nCUBE_Y : 64\nCUBE_Z : 64\nSECONDS : 1.5\nFPS : 66\n"
+                        "MLUPS : %g\nBANDWIDTH : 1\n\n" % (i, nproc, m))
+    res = bm.analyse(sorted(str(p) for p in tmp_path.glob("*.ini")), peak_gbs=1000.0)
+    assert res[1]["MLUPS"] == 105.0 and res[2]["MLUPS"] == 195.0 and res[2]["NUM_EXP"] == 2
+    assert abs(res[2]["SPEEDUP"] - 195.0 / 105.0) < 1e-12 and abs(res[2]["EFFICIENCY"] - 195.0 / 210.0) < 1e-12
+    assert abs(res[1]["ROOFLINE_FRAC_PER_GPU"] - 105.0 * 156.0 / 1e3 / 1000.0) < 1e-12

@@ -20,6 +20,8 @@
 #ifndef LBM_B200_HOST_CCONTROLLER_HPP
 #define LBM_B200_HOST_CCONTROLLER_HPP
 
+#include <sys/stat.h>
+
 #include <chrono>
 #include <cstdlib>
 #include <fstream>
@@ -34,6 +36,7 @@
 #include "CConfiguration.hpp"
 #include "CDomain.hpp"
 #include "CLbmSolver.hpp"
+#include "CLbmVisualizationVTK.hpp"
 #include "CRankWorld.hpp"
 #include "common.h"
 
@@ -253,15 +256,26 @@ public:
 		double floats_per_cell = 19.0 * 2.0 + 1.0;
 		if (cfg->do_visualization || cfg->debug_mode) floats_per_cell += 3;
 
+		/* optional per-step VTK dump (src/CController.hpp:419-436): output/vtk/OUTPUT.<uid>.<step>.vtk */
+		CLbmVisualizationVTK<T> *cLbmVisualization = NULL;
+		if (cfg->do_visualization) {
+			mkdir("output", 0755);
+			mkdir(VTK_OUTPUT_DIR, 0755);
+			cLbmVisualization = new CLbmVisualizationVTK<T>(_UID, std::string("./") + VTK_OUTPUT_DIR + "/OUTPUT");
+			cLbmVisualization->setup(cLbmPtr);
+		}
+
 		connectFaces();
 		cLbmPtr->wait();
 		if (_world) _world->barrier();
 		const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
 		for (int i = 0; i < loops; i++) {
 			computeNextStep();
+			if (cLbmVisualization) cLbmVisualization->render(i);
 			if (cLbmPtr->error()) { std::cerr << cLbmPtr->error.getString(); if (_world) _world->fail(); return EXIT_FAILURE; }
 		}
 		cLbmPtr->wait();
+		delete cLbmVisualization;
 		seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
 		const double gtime = (_world && _UID >= 0) ? _world->reduceMax(seconds) : seconds;

@@ -44,7 +44,8 @@ static void usage(const char *argv0)
 		<< "		[-d device_num]	(-1: list available devices, or first device of the run)" << std::endl
 		<< "		[-k work group size of the reference kernels, default: 128]	(selects the shipped beta kernel's x-shift only)" << std::endl
 		<< "		[-t timestep]	(default: -1 for automatic detection)" << std::endl
-		<< "		[-R list] [-T list] [-g] [-s]	(accepted for compatibility, ignored)" << std::endl
+		<< "		[-g]	(write output/vtk/OUTPUT.<rank>.<step>.vtk every step, default: disabled)" << std::endl
+		<< "		[-R list] [-T list] [-s]	(accepted for compatibility, ignored)" << std::endl
 		<< "		[-c conf.xml]	read the configuration file (replaces all of the above)" << std::endl
 		<< "		[--double] [--smagorinsky C_s] [--sync p2p|copy|host] [--beta-order shipped|linear]" << std::endl
 		<< "		[--validate] [--dump-layout] [--dump-params] [--dump-velocity FILE]" << std::endl;
@@ -238,7 +239,7 @@ int main(int argc, char **argv)
 		case 'G': gravitation_y = atof(optarg); break;
 		case 't': timestep = atof(optarg); break;
 		case 'v': opt.debug = true; break;
-		case 'g': do_visualisation = false; break;      /* VTK output is outside the hot path */
+		case 'g': do_visualisation = true; break;       /* per-step VTK files under output/vtk */
 		case 's': case 'R': case 'T': break;
 		case 'u': std::cerr << "unit tests live in tests/ (pytest); -u is not supported" << std::endl; return -1;
 		case 'c': use_config_file = true; conf_file = optarg; break;
