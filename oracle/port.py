@@ -1,7 +1,7 @@
 """ctypes driver for oracle/liblbm_oracle.so (the plain-C restatement) -- TEST INFRASTRUCTURE ONLY.
 
 ``OracleSolver`` has the same CLbmSolver-shaped interface as ``oracle.ref.RefSolver`` so
-the two can be run side by side (tests/test_oracle_vs_ref.py) and so either can stand in
+the two can be run side by side (tests/test_oracle.py) and so either can stand in
 for a sub-domain in ``oracle.multi``.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline legs may import this module; the product never does.
 """

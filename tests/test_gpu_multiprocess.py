@@ -1,0 +1,60 @@
+"""One process per GPU (torchrun), the layout bench.py measures: every halo transport of the
+product -- one-sided NVLink peer stores over CUDA IPC ("p2p"), NCCL send/recv with and without
+the shell/interior overlap ("overlap", "device"), and the reference's host-staged algorithm
+("host") -- must reproduce the oracle's decomposed run bit for bit on EVERY population of every
+rank (ghost layers included).  Needs >= 2 GPUs on the box; skipped otherwise."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import bits_equal
+from oracle import multi as omulti
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _gpus():
+    import ctypes
+    from turbulent_lbm_multigpu_b200 import capi
+    n = ctypes.c_int(0)
+    capi.load().lbmGetDeviceCount(ctypes.byref(n))
+    return n.value
+
+
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("D,nums,steps,sync", [
+    ((32, 32, 48), (1, 1, 2), 21, "p2p"), ((32, 32, 48), (1, 1, 2), 21, "overlap"),
+    ((32, 32, 48), (1, 1, 2), 20, "device"), ((32, 32, 48), (1, 1, 2), 21, "host"),
+    ((96, 32, 32), (2, 1, 1), 20, "p2p"), ((96, 32, 32), (2, 1, 1), 21, "overlap"),
+    ((32, 32, 64), (1, 2, 2), 15, "p2p"),
+])
+def test_torchrun_ranks_equal_oracle(tmp_path, D, nums, steps, sync):
+    world = nums[0] * nums[1] * nums[2]
+    if _gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    env = dict(os.environ, LBM_TEST_DOMAIN=",".join(map(str, D)), LBM_TEST_NUMS=",".join(map(str, nums)),
+               LBM_TEST_STEPS=str(steps), LBM_TEST_SYNC=sync, LBM_TEST_OUT=str(tmp_path))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "_gpu_rank_worker.py")]
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:]
+    make, po = omulti.make_oracle_factory(D, nums, (0.1, 0.1, 0.1), dtype=np.float32, variant=1)
+    md = omulti.MultiDomain(D, nums, make, slots="reference" if sync == "host" else "minimal")
+    md.run(steps)
+    for rank in range(world):
+        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        o = md.ranks[rank]["solver"]
+        assert bits_equal(z["flags"], o.flags), rank
+        assert bits_equal(z["dd"], o.dd), (rank, sync)
