@@ -157,8 +157,10 @@ def scenario(n_gpus, size=SIZE, scaling="weak", decomp="slab", cs=CS):
 
 
 # ====================================================================== reference arm
-def cpu_reference(size, budget_s=12.0, threads=None, dtype=np.float32):
-    """The reference's kernels (oracle/_ref) on the host cores: bounded sample of the workload."""
+def cpu_reference(size, budget_s=12.0, threads=None, dtype=np.float32, steps=None, warmup=2):
+    """The reference's kernels (oracle/_ref) on the host cores: bounded sample of the workload.
+    steps=None: as many steps as fit in budget_s (the cpu_baseline leg of the GPU arm);
+    steps=K: exactly K timed steps after `warmup` untimed ones (the --impl reference arm)."""
     from oracle import ref
     from turbulent_lbm_multigpu_b200.skeleton import compute_parameters
     p = compute_parameters((size,) * 3, (0.1,) * 3, dtype=np.float32)
@@ -173,12 +175,14 @@ def cpu_reference(size, budget_s=12.0, threads=None, dtype=np.float32):
     s = ref.RefSolver((size,) * 3, [1] * 6, p.inv_tau, p.gravitation, p.u_lid, variant=ref.NOSHM, fast=fast)
     rect = (size - 2, 1, size - 2)
     s.setFlags(np.full(rect[0] * rect[2], 4, np.int32), (1, size - 2, 1), rect)
-    s.simulationStep(); s.simulationStep()          # warm-up (one beta, one alpha)
-    t0 = time.perf_counter()
-    s.simulationStep(); s.simulationStep()
-    per = (time.perf_counter() - t0) / 2
-    steps = max(2, int(budget_s / max(per, 1e-6)) // 2 * 2)
-    steps = min(steps, 200)
+    for _ in range(max(2, warmup)):                 # warm-up (whole beta/alpha cycles first)
+        s.simulationStep()
+    if steps is None:
+        t0 = time.perf_counter()
+        s.simulationStep(); s.simulationStep()
+        per = (time.perf_counter() - t0) / 2
+        steps = max(2, int(budget_s / max(per, 1e-6)) // 2 * 2)
+        steps = min(steps, 200)
     t0 = time.perf_counter()
     for _ in range(steps):
         s.simulationStep()
@@ -190,17 +194,43 @@ def cpu_reference(size, budget_s=12.0, threads=None, dtype=np.float32):
     return dict(value=mlups, unit="MLUPS", cores=cores, kind=kind, sample=sample), dt / steps * 1e3, steps
 
 
+def reference_sample_size(steps, warmup, threads, limit_s=150.0):
+    """Edge of the cubic cavity one reference-arm step runs on: the 256^3 workload itself when
+    `warmup + steps` of it fit in limit_s on these host cores, else the largest of 192/128/96/64
+    that does (MLUPS is a rate, the sample only bounds the wall clock).  Calibrated with two
+    64^3 steps: cost per step scales with the cell count."""
+    from oracle import ref
+    from turbulent_lbm_multigpu_b200.skeleton import compute_parameters
+    fast = ref.available(fast=True)
+    lib = ref.load(fast=fast)
+    if threads:
+        lib.ref_set_threads(threads)
+    p = compute_parameters((64,) * 3, (0.1,) * 3, dtype=np.float32)
+    s = ref.RefSolver((64,) * 3, [1] * 6, p.inv_tau, p.gravitation, p.u_lid, variant=ref.NOSHM, fast=fast)
+    s.simulationStep(); s.simulationStep()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        s.simulationStep()
+    per_cell = (time.perf_counter() - t0) / 4 / 64 ** 3 * 1.5        # in-cache calibration: be pessimistic
+    for size in (256, 192, 128, 96, 64):
+        if per_cell * size ** 3 * (steps + max(2, warmup)) <= limit_s:
+            return size
+    return 64
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # the CPU sample is always the 256^3 single-domain cavity (the reference's fp32 build)
     # torchrun exports OMP_NUM_THREADS=1: the reference arm uses every host core it may run on
-    cb, ms, steps = cpu_reference(min(args.size, 256), budget_s=max(4.0, min(60.0, 0.15 * args.steps)),
-                                  threads=len(os.sched_getaffinity(0)))
+    threads = len(os.sched_getaffinity(0))
+    K, W = max(1, args.steps), max(0, args.warmup)
+    size = reference_sample_size(K, W, threads)
+    size = min(size, args.size)
+    cb, ms, steps = cpu_reference(size, threads=threads, steps=K, warmup=W)
     line = {
         "impl": "reference", "metric": "MLUPS", "value": cb["value"], "unit": "MLUPS", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 2, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
+        "steps": steps, "warmup": max(2, W), "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "cpu_baseline": cb,

@@ -205,6 +205,26 @@ int lbmTimerStop(lbm_t h, float *milliseconds);   /* synchronises */
 
 /* number of kernel launches issued by this handle since creation (bench gpu_launches) */
 int lbmGetLaunchCount(lbm_t h, uint64_t *launches);
+
+/* ---- per-kernel device timeline (replaces the reference's PROFILE build: the OpenCL queue's
+ *      CL_QUEUE_PROFILING_ENABLE + one CProfilerEvent per enqueue, src/libcl/CCL.hpp:1244-1245,
+ *      1752-1778; src/libtools/CProfilerEvent.hpp:29-38, CProfiler.hpp:35-48).
+ *      LBM_PROFILE_EVENTS: every kernel launch of this handle is bracketed by CUDA events on its
+ *      stream (nothing blocks; the reference waits after each enqueue); LBM_PROFILE_NVTX: every
+ *      launch sits in an NVTX range.  Names are the reference's kernel names -- init_kernel,
+ *      lbm_kernel_alpha, lbm_kernel_beta, copy_buffer_rect -- plus lbm_kernel_beta.wrap,
+ *      halo_push, halo_pull, checksum_kernel for the kernels the reference does not have.
+ *      Times are nanoseconds since lbmProfileEnable / lbmProfileClear.  The environment
+ *      variable LBM_B200_PROFILE=<mode> enables it from lbmCreate on (init_kernel included).
+ *      Not usable while the launches are being captured into a CUDA graph. ---------------- */
+#define LBM_PROFILE_EVENTS 1
+#define LBM_PROFILE_NVTX 2
+int lbmProfileEnable(lbm_t h, int mode);          /* 0 = off */
+int lbmProfileClear(lbm_t h);                     /* synchronises, drops the recorded events, new time zero */
+int lbmProfileEventCount(lbm_t h, uint64_t *count, uint64_t *dropped /* may be NULL */);
+int lbmProfileGetEvent(lbm_t h, uint64_t index, char *name, size_t name_bytes,
+		uint64_t *start_ns, uint64_t *end_ns);    /* synchronises on that event */
+
 /* resolved launch configuration (cells per thread, block size, active work-group quirk) */
 int lbmGetConfig(lbm_t h, int *vector_width, int *block_size, int *wg_quirk);
 

@@ -17,6 +17,7 @@ LBM_BETA_ORDER_SHIPPED, LBM_BETA_ORDER_LINEAR = 0, 1
 LBM_HALO_SLOTS_REFERENCE, LBM_HALO_SLOTS_MINIMAL = 0, 1
 LBM_SYNC_ALPHA, LBM_SYNC_BETA = 0, 1
 LBM_BUF_DD, LBM_BUF_FLAGS, LBM_BUF_VELOCITY, LBM_BUF_DENSITY = 0, 1, 2, 3
+LBM_PROFILE_EVENTS, LBM_PROFILE_NVTX = 1, 2
 
 c_int3 = ctypes.c_int * 3
 
@@ -98,6 +99,10 @@ SYMBOLS = {
     "lbmTimerStop": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "lbmGetLaunchCount": (_i, [_vp, ctypes.POINTER(_u64)]),
     "lbmGetConfig": (_i, [_vp, _ip, _ip, _ip]),
+    "lbmProfileEnable": (_i, [_vp, _i]),
+    "lbmProfileClear": (_i, [_vp]),
+    "lbmProfileEventCount": (_i, [_vp, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
+    "lbmProfileGetEvent": (_i, [_vp, _u64, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
 }
 
 _lib = None

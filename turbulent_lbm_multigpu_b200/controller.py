@@ -266,6 +266,14 @@ class CController:
                 self.vector_checksum = s.getVelocityChecksum()
                 print("Checksum: %.8f" % (float(self.vector_checksum) * 1000.0))
             print("done.")
+        # PROFILE block of src/CController.hpp:503-519 (run-time switch: LBM_B200_PROFILE, or
+        # CLbmSolver.profileEnable before run)
+        if s.profileEventCount()[0] > 0:
+            from .profiler import CProfiler, profile_file_name
+            self.profiler = CProfiler()
+            self.profiler.collect(s)
+            nproc = int(np.prod(cfg.subdomain_num))
+            self.profiler.saveProfile(profile_file_name(nproc, self._UID), nproc, self._UID)
         return 0
 
     def addCommunication(self, comm: CComm):

@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   /* header-only NVTX v3: no link dependency */
+
 using namespace lbm;
 
 namespace {
@@ -65,6 +67,14 @@ struct lbm_solver {
 	bool smag;
 	double u_lid;
 	std::string error;
+	/* per-kernel device timeline (replaces CL_QUEUE_PROFILING_ENABLE + CProfilerEvent,
+	 * src/libcl/CCL.hpp:1752-1778, src/libtools/CProfilerEvent.hpp:29-38) */
+	int profile_mode;            /* LBM_PROFILE_EVENTS | LBM_PROFILE_NVTX */
+	cudaEvent_t prof_base;       /* time zero: recorded on the compute stream by lbmProfileEnable */
+	struct prof_rec { const char *name; cudaEvent_t e0, e1; };
+	std::vector<prof_rec> prof;
+	std::vector<cudaEvent_t> prof_pool;   /* recycled by lbmProfileClear */
+	uint64_t prof_dropped;
 };
 
 namespace {
@@ -88,6 +98,41 @@ int fail(lbm_t h, int code, const std::string &msg)
 
 int use_device(lbm_t h) { CUDA_TRY(h, cudaSetDevice(h->device)); return LBM_OK; }
 
+const size_t kProfMaxEvents = 1u << 18;
+
+cudaEvent_t prof_event(lbm_t h)
+{
+	cudaEvent_t e = NULL;
+	if (!h->prof_pool.empty()) { e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
+	if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return NULL; }
+	return e;
+}
+
+/* Brackets ONE kernel launch: counts it and, when profiling is on, gives it an NVTX range and a
+ * pair of CUDA events on the launching stream.  Unlike the reference (clWaitForEvents after every
+ * enqueue, CCL.hpp:1765) nothing blocks: the events are resolved when they are read. */
+struct LaunchScope {
+	lbm_t h; cudaStream_t s; cudaEvent_t e1; bool nvtx;
+	LaunchScope(lbm_t h_, const char *name, cudaStream_t s_) : h(h_), s(s_), e1(NULL), nvtx(false)
+	{
+		if (!h->profile_mode) return;
+		if (h->profile_mode & LBM_PROFILE_NVTX) { nvtxRangePushA(name); nvtx = true; }
+		if (h->profile_mode & LBM_PROFILE_EVENTS) {
+			if (h->prof.size() >= kProfMaxEvents) { h->prof_dropped++; return; }
+			cudaEvent_t e0 = prof_event(h); e1 = prof_event(h);
+			if (!e0 || !e1) { if (e0) h->prof_pool.push_back(e0); if (e1) h->prof_pool.push_back(e1); e1 = NULL; h->prof_dropped++; return; }
+			cudaEventRecord(e0, s);
+			h->prof.push_back(lbm_solver::prof_rec{ name, e0, e1 });
+		}
+	}
+	~LaunchScope()
+	{
+		h->launches++;
+		if (e1) cudaEventRecord(e1, s);
+		if (nvtx) nvtxRangePop();
+	}
+};
+
 template <typename T>
 StepParams<T> make_params(lbm_t h, const Box &b)
 {
@@ -110,8 +155,8 @@ StepParams<T> make_params(lbm_t h, const Box &b)
 template <typename T, int VEC, bool SMAG, bool STORE>
 void launch_alpha(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStream_t s, cudaStream_t)
 {
+	LaunchScope ls(h, "lbm_kernel_alpha", s);
 	lbm_alpha_kernel<T, VEC, SMAG, STORE><<<grid, block, 0, s>>>(P);
-	h->launches++;
 }
 
 template <typename T, int VEC, bool SMAG, bool STORE>
@@ -139,16 +184,16 @@ void launch_beta(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStr
 		else { Q.z0 = ranges[1][0]; Q.zsplit = 0x7fffffff; Q.zjump = 0; }
 		Q.nz = nlo + nhi;
 		dim3 g2(grid.x, (unsigned)Q.nz);
+		LaunchScope ls(h, "lbm_kernel_beta.wrap", sg);
 		if (shipped) lbm_beta_general_kernel<T, VEC, SMAG, STORE, 0><<<g2, block, 0, sg>>>(Q);
 		else lbm_beta_general_kernel<T, VEC, SMAG, STORE, 1><<<g2, block, 0, sg>>>(Q);
-		h->launches++;
 	}
 	/* the vectorised kernel second: when sg is another stream the small wrapping kernel is
 	 * already resident and both run side by side */
 	if (P.wg == 0) {   /* with the work-group quirk live every block takes the general path */
+		LaunchScope ls(h, "lbm_kernel_beta", s);
 		if (shipped) lbm_beta_kernel<T, VEC, SMAG, STORE, 0><<<grid, block, 0, s>>>(P);
 		else lbm_beta_kernel<T, VEC, SMAG, STORE, 1><<<grid, block, 0, s>>>(P);
-		h->launches++;
 	}
 }
 
@@ -265,8 +310,8 @@ void launch_rect(lbm_t h, const T *src, T *dst, const RectCopy &R, cudaStream_t 
 	long long grid = (total + block - 1) / block;
 	if (grid > 148LL * 16) grid = 148LL * 16;
 	if (grid < 1) grid = 1;
+	LaunchScope ls(h, "copy_buffer_rect", s);
 	rect_copy_kernel<T><<<(unsigned)grid, block, 0, s>>>(src, dst, R);
-	h->launches++;
 }
 
 void launch_rect_bytes(lbm_t h, size_t elem, const void *src, void *dst, const RectCopy &R, cudaStream_t s)
@@ -417,6 +462,7 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	h->dd = h->velocity = h->density = NULL; h->flags = NULL;
 	h->staging = NULL; h->staging_bytes = 0; h->d_checksum = NULL;
 	h->counter = 0; h->launches = 0; h->step_aux = NULL;
+	h->profile_mode = 0; h->prof_base = NULL; h->prof_dropped = 0;
 	h->xshell = 32;
 	if (const char *e = getenv("LBM_B200_XSHELL")) h->xshell = atoi(e) > 1 ? atoi(e) : 2;
 	h->sync_seq[0] = h->sync_seq[1] = 0;
@@ -461,6 +507,9 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	if (d->store_density) { CREATE_TRY(cudaMalloc(&h->density, (size_t)h->n * h->elem)); }
 #undef CREATE_TRY
 	*out = h;
+	/* LBM_B200_PROFILE=1|2|3: the reference's compile-time PROFILE switch (SConstruct) as a run-time
+	 * one, on from the first launch so that init_kernel is on the timeline too */
+	if (const char *e = getenv("LBM_B200_PROFILE")) if (atoi(e) > 0) lbmProfileEnable(h, atoi(e) & 3);
 	int rc = lbmReset(h);
 	if (rc != LBM_OK) { std::string m = h->error; lbmDestroy(h); *out = NULL; return fail(NULL, rc, m); }
 	return LBM_OK;
@@ -484,6 +533,9 @@ int lbmDestroy(lbm_t h)
 	if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
 	if (h->ev_t0) cudaEventDestroy(h->ev_t0);
 	if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+	for (size_t i = 0; i < h->prof.size(); i++) { cudaEventDestroy(h->prof[i].e0); cudaEventDestroy(h->prof[i].e1); }
+	for (size_t i = 0; i < h->prof_pool.size(); i++) cudaEventDestroy(h->prof_pool[i]);
+	if (h->prof_base) cudaEventDestroy(h->prof_base);
 	if (h->own_compute && h->compute) cudaStreamDestroy(h->compute);
 	if (h->own_comm && h->comm) cudaStreamDestroy(h->comm);
 	delete h;
@@ -498,6 +550,8 @@ int lbmReset(lbm_t h)
 	const int block = 256;
 	const unsigned grid = (unsigned)((h->n + block - 1) / block);
 	const int *bc = h->desc.bc;
+	{
+	LaunchScope ls(h, "init_kernel", h->compute);
 	if (h->dtype == LBM_F32)
 		lbm_init_kernel<float><<<grid, block, 0, h->compute>>>((float *)h->dd, h->flags, (float *)h->velocity,
 				(float *)h->density, h->n, h->stride, h->sx, h->sy, h->sz, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5],
@@ -506,7 +560,7 @@ int lbmReset(lbm_t h)
 		lbm_init_kernel<double><<<grid, block, 0, h->compute>>>((double *)h->dd, h->flags, (double *)h->velocity,
 				(double *)h->density, h->n, h->stride, h->sx, h->sy, h->sz, bc[0], bc[1], bc[2], bc[3], bc[4], bc[5],
 				h->velocity != NULL, h->density != NULL);
-	h->launches++;
+	}
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
 }
@@ -712,11 +766,13 @@ int lbmChecksumVelocity(lbm_t h, double *out, int host_order)
 	}
 	CUDA_TRY(h, cudaMemsetAsync(h->d_checksum, 0, sizeof(double), h->compute));
 	const int block = 256, grid = 148 * 8;
+	{
+	LaunchScope ls(h, "checksum_kernel", h->compute);
 	if (h->dtype == LBM_F32)
 		checksum_kernel<float><<<grid, block, 0, h->compute>>>((const float *)h->velocity, h->flags, h->n, h->d_checksum);
 	else
 		checksum_kernel<double><<<grid, block, 0, h->compute>>>((const double *)h->velocity, h->flags, h->n, h->d_checksum);
-	h->launches++;
+	}
 	CUDA_TRY(h, cudaGetLastError());
 	CUDA_TRY(h, cudaMemcpyAsync(out, h->d_checksum, sizeof(double), cudaMemcpyDeviceToHost, h->compute));
 	CUDA_TRY(h, cudaStreamSynchronize(h->compute));
@@ -883,9 +939,11 @@ int axis_push(lbm_t h, int kind, int axis, cudaStream_t s)
 	}
 	if (nf == 0) return LBM_OK;
 	dim3 grid(blocks, nf);
+	{
+	LaunchScope ls(h, "halo_push", s);
 	if (h->dtype == LBM_F32) halo_push_kernel<float><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
 	else halo_push_kernel<double><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
-	h->launches++;
+	}
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
 }
@@ -917,9 +975,11 @@ int axis_pull(lbm_t h, int kind, int axis, cudaStream_t s)
 	}
 	if (nf == 0) return LBM_OK;
 	dim3 grid(blocks, nf);
+	{
+	LaunchScope ls(h, "halo_pull", s);
 	if (h->dtype == LBM_F32) halo_pull_kernel<float><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
 	else halo_pull_kernel<double><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
-	h->launches++;
+	}
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
 }
@@ -1169,6 +1229,60 @@ int lbmGetLaunchCount(lbm_t h, uint64_t *launches)
 	CHECK_HANDLE(h);
 	if (!launches) return fail(h, LBM_ERR_INVALID, "null launches");
 	*launches = h->launches;
+	return LBM_OK;
+}
+
+int lbmProfileEnable(lbm_t h, int mode)
+{
+	CHECK_HANDLE(h);
+	if (mode < 0 || mode > (LBM_PROFILE_EVENTS | LBM_PROFILE_NVTX)) return fail(h, LBM_ERR_INVALID, "invalid profile mode");
+	if (int rc = use_device(h)) return rc;
+	if ((mode & LBM_PROFILE_EVENTS) && !h->prof_base) {
+		CUDA_TRY(h, cudaEventCreate(&h->prof_base));
+		CUDA_TRY(h, cudaEventRecord(h->prof_base, h->compute));
+	}
+	h->profile_mode = mode;
+	return LBM_OK;
+}
+
+int lbmProfileClear(lbm_t h)
+{
+	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	CUDA_TRY(h, cudaStreamSynchronize(h->compute));
+	CUDA_TRY(h, cudaStreamSynchronize(h->comm));
+	for (size_t i = 0; i < h->prof.size(); i++) { h->prof_pool.push_back(h->prof[i].e0); h->prof_pool.push_back(h->prof[i].e1); }
+	h->prof.clear();
+	h->prof_dropped = 0;
+	if (h->prof_base) CUDA_TRY(h, cudaEventRecord(h->prof_base, h->compute));
+	return LBM_OK;
+}
+
+int lbmProfileEventCount(lbm_t h, uint64_t *count, uint64_t *dropped)
+{
+	CHECK_HANDLE(h);
+	if (!count) return fail(h, LBM_ERR_INVALID, "null count");
+	*count = h->prof.size();
+	if (dropped) *dropped = h->prof_dropped;
+	return LBM_OK;
+}
+
+int lbmProfileGetEvent(lbm_t h, uint64_t index, char *name, size_t name_bytes, uint64_t *start_ns, uint64_t *end_ns)
+{
+	CHECK_HANDLE(h);
+	if (index >= h->prof.size()) return fail(h, LBM_ERR_INVALID, "profile event index out of range");
+	if (int rc = use_device(h)) return rc;
+	const lbm_solver::prof_rec &r = h->prof[index];
+	CUDA_TRY(h, cudaEventSynchronize(r.e1));
+	float t0 = 0, t1 = 0;
+	CUDA_TRY(h, cudaEventElapsedTime(&t0, h->prof_base, r.e0));
+	CUDA_TRY(h, cudaEventElapsedTime(&t1, h->prof_base, r.e1));
+	if (t0 < 0) t0 = 0;
+	if (t1 < t0) t1 = t0;
+	if (name && name_bytes > 0) { strncpy(name, r.name, name_bytes - 1); name[name_bytes - 1] = 0; }
+	/* CL_PROFILING_COMMAND_START/END are nanoseconds (CProfilerEvent.hpp:31-35) */
+	if (start_ns) *start_ns = (uint64_t)((double)t0 * 1e6 + 0.5);
+	if (end_ns) *end_ns = (uint64_t)((double)t1 * 1e6 + 0.5);
 	return LBM_OK;
 }
 

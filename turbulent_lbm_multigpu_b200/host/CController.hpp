@@ -37,6 +37,7 @@
 #include "CDomain.hpp"
 #include "CLbmSolver.hpp"
 #include "CLbmVisualizationVTK.hpp"
+#include "CProfiler.hpp"
 #include "CRankWorld.hpp"
 #include "common.h"
 
@@ -189,6 +190,7 @@ class CController {
 public:
 	float vector_checksum;
 	double seconds, mlups;          /* filled by run() */
+	CProfiler profiler;             /* per rank (the reference's ProfilerSingleton is per MPI process) */
 	int halo_slots;                 /* LBM_HALO_SLOTS_MINIMAL (5 per face) | _REFERENCE (19) */
 	int beta_order;
 
@@ -314,6 +316,20 @@ public:
 				std::cout << std::resetiosflags(std::ios::fixed);
 			}
 			std::cout << "done." << std::endl;
+		}
+
+		/* PROFILE block of src/CController.hpp:503-519: output/profile/profile_<np>_<uid>.ini.  The
+		 * reference's compile-time switch is the run-time variable LBM_B200_PROFILE (read by lbmCreate). */
+		uint64_t prof_events = 0;
+		if (lbmProfileEventCount(cLbmPtr->handle(), &prof_events, NULL) == LBM_OK && prof_events > 0) {
+			mkdir("output", 0755);
+			mkdir(PROFILE_OUTPUT_DIR, 0755);
+			std::ostringstream profile_file_name;
+			profile_file_name << "./" << PROFILE_OUTPUT_DIR << "/" << "profile_" << cfg->subdomain_num.elements()
+			                  << "_" << _UID << ".ini";
+			if (profiler.collect(cLbmPtr->handle()) != LBM_OK)
+				std::cerr << "profile: " << lbmGetLastErrorString(cLbmPtr->handle()) << std::endl;
+			profiler.saveProfile(profile_file_name.str(), cfg->subdomain_num.elements(), _UID);
 		}
 		return EXIT_SUCCESS;
 	}

@@ -318,6 +318,28 @@ class CLbmSolver:
         self._ck(self._lib.lbmGetLaunchCount(self._h, ctypes.byref(c)))
         return c.value
 
+    # per-kernel device timeline (the reference's PROFILE build, src/libcl/CCL.hpp:1752-1778)
+    def profileEnable(self, mode=capi.LBM_PROFILE_EVENTS):
+        self._ck(self._lib.lbmProfileEnable(self._h, int(mode)))
+
+    def profileClear(self):
+        self._ck(self._lib.lbmProfileClear(self._h))
+
+    def profileEventCount(self):
+        n, d = ctypes.c_uint64(), ctypes.c_uint64()
+        self._ck(self._lib.lbmProfileEventCount(self._h, ctypes.byref(n), ctypes.byref(d)))
+        return n.value, d.value
+
+    def profileEvents(self):
+        """[(kernel name, start_ns, end_ns)] since profileEnable / profileClear; synchronises"""
+        out = []
+        name = ctypes.create_string_buffer(128)
+        t0, t1 = ctypes.c_uint64(), ctypes.c_uint64()
+        for i in range(self.profileEventCount()[0]):
+            self._ck(self._lib.lbmProfileGetEvent(self._h, i, name, 128, ctypes.byref(t0), ctypes.byref(t1)))
+            out.append((name.value.decode(), t0.value, t1.value))
+        return out
+
     def config(self):
         v, b, q = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         self._ck(self._lib.lbmGetConfig(self._h, ctypes.byref(v), ctypes.byref(b), ctypes.byref(q)))
