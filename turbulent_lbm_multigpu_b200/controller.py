@@ -268,7 +268,8 @@ class CController:
             print("done.")
         # PROFILE block of src/CController.hpp:503-519 (run-time switch: LBM_B200_PROFILE, or
         # CLbmSolver.profileEnable before run)
-        if s.profileEventCount()[0] > 0:
+        count = getattr(s, "profileEventCount", None)   # an injected solver need not carry the timeline
+        if count is not None and count()[0] > 0:
             from .profiler import CProfiler, profile_file_name
             self.profiler = CProfiler()
             self.profiler.collect(s)
