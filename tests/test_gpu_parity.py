@@ -220,3 +220,22 @@ def test_padded_slot_stride_is_invisible(size, dtype, order, monkeypatch):
     assert bits_equal(got, full2)
     c.setDensityDistribution(o.dd)          # whole-array upload through the pitched copy
     assert bits_equal(c.storeDensityDistribution(), o.dd)
+
+
+def test_debug_print_dumps_the_device_arrays():
+    """reference src/CLbmSolver.hpp:1032-1101: debug_print / debugDD show what the store* calls return."""
+    import io
+    from turbulent_lbm_multigpu_b200 import debug
+    c = make_cuda((8, 8, 8), np.float32)
+    for _ in range(3):
+        c.simulationStep()
+    buf = io.StringIO()
+    c.debug_print(file=buf)
+    assert buf.getvalue() == debug.debug_print(c.storeDensityDistribution(), c.storeVelocity(), c.storeDensity(),
+                                               c.storeFlags())
+    assert buf.getvalue().count("\n0: ") == 4 and "FLAGS:\n0: 1 0 0 0 1 0 0 0 " in buf.getvalue()
+    buf = io.StringIO()
+    c.debugDD(18, 16, 64, file=buf)
+    rest = c.storeDensityDistribution().reshape(19, -1)[18]
+    assert buf.getvalue().split()[1] == "%.4f" % float(rest[0]) and buf.getvalue().startswith("%d: " % (18 * 512 // 16))
+    c.close()

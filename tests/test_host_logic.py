@@ -178,3 +178,45 @@ def test_halo_slot_masks():
         expect = [f for f in range(19) if sum(a * b for a, b in zip(d, LBM_UNITS[f])) > 0]
         assert mask(capi.LBM_SYNC_BETA, d, capi.LBM_HALO_SLOTS_MINIMAL) == expect
 
+
+
+@pytest.mark.parametrize("tname,dtype", [("float", np.float32), ("double", np.float64)])
+def test_debug_dumps_follow_the_reference_format(tmp_path, tname, dtype):
+    """debug_print / debugDD (reference src/CLbmSolver.hpp:981-1101): the C++ helper
+    (host/CLbmDebug.hpp) and the Python twin (debug.py) print the same bytes; the layout is pinned by
+    hand-written lines restating the reference's loops ("\\n<row>: " every `wrap` values, precision 4
+    fixed, flags dumped byte-wise, blank line every `empty_line` values in debugDD)."""
+    import subprocess
+    from turbulent_lbm_multigpu_b200 import debug
+    exe = str(tmp_path / "debug_print")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-Wall",
+                           os.path.join(ROOT, "tests", "cpp", "debug_print.cpp"), "-o", exe])
+    got = subprocess.check_output([exe] + (["double"] if tname == "double" else []), text=True)
+
+    cells = 12
+    T = dtype
+    a = np.arange(19 * cells, dtype=np.uint64)
+    dd = (((a * 2654435761) & 0xffffffff) >> 9).astype(np.int64) % 4001 - 2000
+    dd = dd.astype(T) / T(7919)
+    a = np.arange(3 * cells, dtype=np.uint64)
+    vel = ((((a * 40503) & 0xffffffff) >> 2).astype(np.int64) % 2001 - 1000).astype(T) / T(100000)
+    rho = T(1) + (np.arange(cells) - 5).astype(T) / T(3000)
+    fl = (1 << ((np.arange(cells) * 7) % 4)).astype(np.int32)
+    fl[3] = -2
+    exp = ("0.123457\n" + debug.debug_print(dd, vel, rho, fl) + "DD 5\n" + debug.debugDD(dd, cells, 5, 16, 6)
+           + debug.debugDD(dd, cells, 0) + "0.123457\n")
+    assert got == exp
+    # the layout itself, restated by hand from the reference's loops
+    lines = got.split("\n")
+    assert lines[1] == "DENSITY DISTRIBUTIONS:" and lines[2].startswith("0: ") and lines[3].startswith("1: ")
+    assert len(lines[2].split()) == 1 + 16 and all(len(t.split(".")[1]) == 4 for t in lines[2].split()[1:])
+    i = lines.index("VELOCITY:")
+    assert lines[i - 1] == "" and len(lines[i + 1].split()) == 1 + 12
+    i = lines.index("DENSITY:")
+    assert len(lines[i + 1].split()) == 1 + 4 and lines[i + 1].split()[1] == "%.4f" % float(rho[0])
+    i = lines.index("FLAGS:")
+    assert lines[i + 1] == "0: 1 0 0 0 8 0 0 0 4 0 0 0 -2 -1 -1 -1 "      # int32 flags byte by byte, signed chars
+    i = lines.index("DD 5")
+    # slot 5 starts at element 60: row labels count from the array start (60 // 16 = 3 appears at element 64)
+    assert lines[i + 1].count(" ") == 4 and not lines[i + 1].startswith("3: ")
+    assert lines[i + 2].startswith("4: ") and "" in lines[i + 1:i + 8]

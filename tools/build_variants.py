@@ -1,24 +1,42 @@
 #!/usr/bin/env python3
-"""Build tuning variants of liblbm_b200.so (different __launch_bounds__) next to the default one."""
+"""Build tuning variants of liblbm_b200.so next to the default one: liblbm_b200_<tag>.so.
+
+Tags: lb<T>x<B> = __launch_bounds__(T, B) on the beta kernel; ld<a>st<b> = cache operators of the
+aligned slot streams (LBM_HINT_LD / LBM_HINT_ST in csrc/lbm_kernels.cuh).  Load one with
+LBM_B200_LIB=<path> (tools/sweep_variants.sh)."""
 import os
+import re
 import sys
 from concurrent.futures import ThreadPoolExecutor
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from turbulent_lbm_multigpu_b200 import build as b  # noqa: E402
 
-VARIANTS = {"lb256x2": (256, 2), "lb128x5": (128, 5), "lb128x6": (128, 6), "lb128x8": (128, 8)}
+DEFAULT = ["lb256x2", "lb128x5", "lb128x6", "lb128x8"]
 
 
-def one(item):
-    tag, lb = item
+def defines(tag):
+    out = []
+    for part in tag.split("_"):
+        m = re.fullmatch(r"lb(\d+)x(\d+)", part)
+        if m:
+            out += ["-DLBM_LB_MAXT=%s" % m.group(1), "-DLBM_LB_MINB=%s" % m.group(2)]
+            continue
+        m = re.fullmatch(r"ld(\d)st(\d)", part)
+        if m:
+            out += ["-DLBM_HINT_LD=%s" % m.group(1), "-DLBM_HINT_ST=%s" % m.group(2)]
+            continue
+        raise SystemExit("unknown variant tag %r" % part)
+    return out
+
+
+def one(tag):
     out = os.path.join(b.LIBDIR, "liblbm_b200_%s.so" % tag)
-    b.build(force=True, extra=["-DLBM_LB_MAXT=%d" % lb[0], "-DLBM_LB_MINB=%d" % lb[1]], out=out)
+    b.build(force=True, extra=defines(tag), out=out)
     return out
 
 
 if __name__ == "__main__":
-    sel = {k: v for k, v in VARIANTS.items() if not sys.argv[1:] or k in sys.argv[1:]}
     with ThreadPoolExecutor(4) as ex:
-        for o in ex.map(one, sel.items()):
+        for o in ex.map(one, sys.argv[1:] or DEFAULT):
             print(o)

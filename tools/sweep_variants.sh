@@ -1,4 +1,7 @@
-for v in "" _lb256x2 _lb128x5 _lb128x6 _lb128x8; do
+#!/bin/bash
+# usage: tools/sweep_variants.sh [tag ...]   -- probe_perf.py over the default library and the named variants
+for v in "" "$@"; do
+  lib=$PWD/turbulent_lbm_multigpu_b200/lib/liblbm_b200${v:+_$v}.so
   echo "=== variant ${v:-default}"
-  LBM_B200_LIB=$PWD/turbulent_lbm_multigpu_b200/lib/liblbm_b200$v.so python tools/probe_perf.py --size 256 --steps 30 --cs 0.0 0.1 --block 64 128 --modes alpha beta
+  LBM_B200_LIB=$lib python tools/probe_perf.py --size ${SIZE:-256} --dtype ${DTYPE:-f32} --steps 40 --cs 0.1 --vw 2 --block 128 --modes alpha beta both
 done

@@ -55,15 +55,46 @@ struct StepParams {
 	int store_v, store_r;    /* write velocity / density arrays (only read when STORE) */
 };
 
-/* ---------------------------------------------------------------- vector access */
+/* ---------------------------------------------------------------- vector access
+ * Cache-operator tuning knobs for the ALIGNED slot streams (each value is touched once per step,
+ * so nothing is lost by not keeping it): LBM_HINT_LD 0 = ld.global (default), 1 = .cs (evict
+ * first), 2 = .cg (L2 only); LBM_HINT_ST 0 = st.global (default), 1 = .cs, 2 = .cg.  The +-1
+ * shifted pieces of beta always use the default operators: they live on L1 reuse. */
+#ifndef LBM_HINT_LD
+#define LBM_HINT_LD 0
+#endif
+#ifndef LBM_HINT_ST
+#define LBM_HINT_ST 0
+#endif
+template <typename V> __device__ __forceinline__ V hinted_load(const V *p)
+{
+#if LBM_HINT_LD == 1
+	return __ldcs(p);
+#elif LBM_HINT_LD == 2
+	return __ldcg(p);
+#else
+	return *p;
+#endif
+}
+template <typename V> __device__ __forceinline__ void hinted_store(V *p, V v)
+{
+#if LBM_HINT_ST == 1
+	__stcs(p, v);
+#elif LBM_HINT_ST == 2
+	__stcg(p, v);
+#else
+	*p = v;
+#endif
+}
+
 template <typename T, int VEC> struct VecIO;
 
 template <> struct VecIO<float, 4> {
 	static __device__ __forceinline__ void load(const float *p, float (&v)[4]) {
-		float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+		float4 t = hinted_load(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 	}
 	static __device__ __forceinline__ void store(float *p, const float (&v)[4]) {
-		*reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+		hinted_store(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
 	}
 	/* p is 4 B past / before a 16 B boundary: 32 + 64 + 32 bit pieces */
 	static __device__ __forceinline__ void load_shifted(const float *p, float (&v)[4]) {
@@ -79,20 +110,20 @@ template <> struct VecIO<float, 4> {
 };
 template <> struct VecIO<float, 2> {
 	static __device__ __forceinline__ void load(const float *p, float (&v)[2]) {
-		float2 t = *reinterpret_cast<const float2 *>(p); v[0] = t.x; v[1] = t.y;
+		float2 t = hinted_load(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y;
 	}
 	static __device__ __forceinline__ void store(float *p, const float (&v)[2]) {
-		*reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+		hinted_store(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
 	}
 	static __device__ __forceinline__ void load_shifted(const float *p, float (&v)[2]) { v[0] = p[0]; v[1] = p[1]; }
 	static __device__ __forceinline__ void store_shifted(float *p, const float (&v)[2]) { p[0] = v[0]; p[1] = v[1]; }
 };
 template <> struct VecIO<double, 2> {
 	static __device__ __forceinline__ void load(const double *p, double (&v)[2]) {
-		double2 t = *reinterpret_cast<const double2 *>(p); v[0] = t.x; v[1] = t.y;
+		double2 t = hinted_load(reinterpret_cast<const double2 *>(p)); v[0] = t.x; v[1] = t.y;
 	}
 	static __device__ __forceinline__ void store(double *p, const double (&v)[2]) {
-		*reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+		hinted_store(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1]));
 	}
 	static __device__ __forceinline__ void load_shifted(const double *p, double (&v)[2]) { v[0] = p[0]; v[1] = p[1]; }
 	static __device__ __forceinline__ void store_shifted(double *p, const double (&v)[2]) { p[0] = v[0]; p[1] = v[1]; }

@@ -4,7 +4,7 @@
  * Same public surface: constructor argument list, public data (drivenCavityVelocity,
  * SIZE_DD_HOST, simulation_step_counter, error + everything inherited from CLbmSkeleton) and
  * methods (reload, reset, simulationStep[Alpha|Beta], wait, addDrivenCavityValue, the store.../set... family
- * in full and rect form, getVelocityChecksum, debug_print).  Every body is one call into
+ * in full and rect form, getVelocityChecksum, debug_print, debugDD).  Every body is one call into
  * liblbm_b200.so (include/lbm_b200.h); a non-zero status becomes `error << message`, the
  * reference's convention (checked by the caller at src/CController.hpp:218-221).  There is no
  * CPU fallback: without a CUDA device reload() records an error.
@@ -21,6 +21,7 @@
 
 #include "../../include/lbm_b200.h"
 #include "CCL.hpp"
+#include "CLbmDebug.hpp"
 #include "CLbmSkeleton.hpp"
 #include "common.h"
 
@@ -169,29 +170,27 @@ public:
 		return v;
 	}
 
-	/* src/CLbmSolver.hpp:985-1100, for tiny domains only */
+	/* src/CLbmSolver.hpp:1032-1057: dump of all four device arrays, for tiny domains only
+	 * (the caller's guard is <= 512 cells, src/CController.hpp:439-443) */
 	void debug_print()
 	{
 		const size_t n = (size_t)this->domain_cells.elements();
 		std::vector<T> dd(n * SIZE_DD_HOST), vel(n * 3), rho(n);
 		std::vector<int> fl(n);
 		storeDensityDistribution(dd.data());
+		storeVelocity(vel.data());
+		storeDensity(rho.data());
 		storeFlags(fl.data());
-		if (store_velocity) storeVelocity(vel.data());
-		if (store_density) storeDensity(rho.data());
-		std::streamsize ss = std::cout.precision();
-		std::cout.precision(4);
-		std::cout.setf(std::ios::fixed, std::ios::floatfield);
-		std::cout << "DENSITY DISTRIBUTIONS [cell][slot]:" << std::endl;
-		for (size_t a = 0; a < n; a++) {
-			for (size_t f = 0; f < SIZE_DD_HOST; f++) std::cout << dd[f * n + a] << "\t";
-			std::cout << "| flag " << fl[a];
-			if (store_velocity) std::cout << " u " << vel[a] << " " << vel[n + a] << " " << vel[2 * n + a];
-			if (store_density) std::cout << " rho " << rho[a];
-			std::cout << std::endl;
-		}
-		std::cout.precision(ss);
-		std::cout << std::resetiosflags(std::ios::fixed);
+		lbm_debug::debugPrint(std::cout, dd.data(), vel.data(), rho.data(), fl.data(), n);
+	}
+
+	/* src/CLbmSolver.hpp:1062-1101: one slot of the populations */
+	void debugDD(size_t dd_id = 0, size_t wrap_size = 16, size_t empty_line = 16)
+	{
+		const size_t n = (size_t)this->domain_cells.elements();
+		std::vector<T> dd(n * SIZE_DD_HOST);
+		storeDensityDistribution(dd.data());
+		lbm_debug::debugDD(std::cout, dd.data(), n, dd_id, wrap_size, empty_line);
 	}
 };
 

@@ -216,6 +216,20 @@ class CLbmSolver:
         self._ck(self._lib.lbmChecksumVelocity(self._h, ctypes.byref(out), int(bool(host_order))))
         return np.float32(out.value) if host_order else out.value
 
+    def debug_print(self, file=None):
+        """reference src/CLbmSolver.hpp:1032-1057 (tiny domains only)."""
+        import sys
+        from . import debug
+        (file or sys.stdout).write(debug.debug_print(self.storeDensityDistribution(), self.storeVelocity(),
+                                                     self.storeDensity(), self.storeFlags()))
+
+    def debugDD(self, dd_id=0, wrap_size=16, empty_line=16, file=None):
+        """reference src/CLbmSolver.hpp:1062-1101."""
+        import sys
+        from . import debug
+        (file or sys.stdout).write(debug.debugDD(self.storeDensityDistribution(), self.domain_cells_count,
+                                                 dd_id, wrap_size, empty_line))
+
     # ---------------------------------------------------------------- device-side halo path
     def haloSlotMask(self, sync_kind, recv_dir, slots=capi.LBM_HALO_SLOTS_MINIMAL):
         m = ctypes.c_uint32()
