@@ -226,7 +226,7 @@ def test_debug_print_dumps_the_device_arrays():
     """reference src/CLbmSolver.hpp:1032-1101: debug_print / debugDD show what the store* calls return."""
     import io
     from turbulent_lbm_multigpu_b200 import debug
-    c = make_cuda((8, 8, 8), np.float32)
+    c = make_cuda((16, 16, 16), np.float32)
     for _ in range(3):
         c.simulationStep()
     buf = io.StringIO()
@@ -237,5 +237,5 @@ def test_debug_print_dumps_the_device_arrays():
     buf = io.StringIO()
     c.debugDD(18, 16, 64, file=buf)
     rest = c.storeDensityDistribution().reshape(19, -1)[18]
-    assert buf.getvalue().split()[1] == "%.4f" % float(rest[0]) and buf.getvalue().startswith("%d: " % (18 * 512 // 16))
+    assert buf.getvalue().split()[1] == "%.4f" % float(rest[0]) and buf.getvalue().startswith("%d: " % (18 * 4096 // 16))
     c.close()

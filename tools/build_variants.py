@@ -2,7 +2,8 @@
 """Build tuning variants of liblbm_b200.so next to the default one: liblbm_b200_<tag>.so.
 
 Tags: lb<T>x<B> = __launch_bounds__(T, B) on the beta kernel; ld<a>st<b> = cache operators of the
-aligned slot streams (LBM_HINT_LD / LBM_HINT_ST in csrc/lbm_kernels.cuh).  Load one with
+aligned slot streams (LBM_HINT_LD / LBM_HINT_ST in csrc/lbm_kernels.cuh); offtab<n> = beta addresses
+from the constant-bank offset table (LBM_BETA_OFFTAB=n); tags combine with '_' (offtab1_lb128x6).  Load one with
 LBM_B200_LIB=<path> (tools/sweep_variants.sh)."""
 import os
 import re
@@ -25,6 +26,10 @@ def defines(tag):
         m = re.fullmatch(r"ld(\d)st(\d)", part)
         if m:
             out += ["-DLBM_HINT_LD=%s" % m.group(1), "-DLBM_HINT_ST=%s" % m.group(2)]
+            continue
+        m = re.fullmatch(r"offtab(\d)", part)
+        if m:
+            out += ["-DLBM_BETA_OFFTAB=%s" % m.group(1)]
             continue
         raise SystemExit("unknown variant tag %r" % part)
     return out

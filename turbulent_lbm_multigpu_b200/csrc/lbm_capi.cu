@@ -149,6 +149,10 @@ StepParams<T> make_params(lbm_t h, const Box &b)
 	else { P.zsplit = 0x7fffffff; P.zjump = 0; }
 	P.wg = h->wg_quirk;
 	P.store_v = h->desc.store_velocity; P.store_r = h->desc.store_density;
+	static const int e[18][3] = { { 1, 0, 0 }, { -1, 0, 0 }, { 0, 1, 0 }, { 0, -1, 0 }, { 1, 1, 0 }, { -1, -1, 0 },
+		{ 1, -1, 0 }, { -1, 1, 0 }, { 1, 0, 1 }, { -1, 0, -1 }, { 1, 0, -1 }, { -1, 0, 1 }, { 0, 1, 1 }, { 0, -1, -1 },
+		{ 0, 1, -1 }, { 0, -1, 1 }, { 0, 0, 1 }, { 0, 0, -1 } };      /* src/main.cpp:38-66 */
+	for (int i = 0; i < 18; i++) P.boff[i] = (long long)i * P.ns + e[i][0] + (long long)e[i][1] * P.sx + (long long)e[i][2] * P.sxy;
 	return P;
 }
 

@@ -53,6 +53,11 @@ struct StepParams {
 	int zsplit, zjump;
 	int wg;                  /* >0: emulate lbm_beta.cl:221-234 work-group x-shift */
 	int store_v, store_r;    /* write velocity / density arrays (only read when STORE) */
+	/* beta: element offset of location (slot i, cell + e_i) from the cell's slot-0 address,
+	 * i*ns + e_i . (1, sx, sxy).  Launch-uniform, so an address is `base + boff[i]` with the
+	 * offset read from the constant bank: cheap to rematerialise for the push, which keeps 18
+	 * 64-bit pointers out of the register file between pull and push (see beta_uses_offset_table) */
+	long long boff[18];
 };
 
 /* ---------------------------------------------------------------- vector access
@@ -534,6 +539,19 @@ __device__ __forceinline__ bool beta_block_is_general(const StepParams<T> &P)
 	return (zb + o0 < reach) || (zb + o1 + reach >= P.n);
 }
 
+/* How the 18 pull/push addresses are formed: from the constant-bank offset table
+ * (StepParams::boff) or from DY/DZ/ns arithmetic.  Same addresses, different instruction
+ * schedule; measured per instantiation (profiles/r1_sweep_beta_offtab.log).
+ * LBM_BETA_OFFTAB: 0 never, 1 always, 2 (default) the measured choice. */
+#ifndef LBM_BETA_OFFTAB
+#define LBM_BETA_OFFTAB 2
+#endif
+template <typename T, bool SMAG>
+__device__ __forceinline__ constexpr bool beta_uses_offset_table()
+{
+	return LBM_BETA_OFFTAB == 1 || (LBM_BETA_OFFTAB == 2 && SMAG && sizeof(T) == 4);
+}
+
 template <typename T, int VEC, bool SMAG, bool STORE, int ORDER>
 __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 {
@@ -548,17 +566,22 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	/* location (slot j, cell c + e_j) is read as d[j^1] and written as d[j] */
 	T *base = P.dd + gid;
 	T *loc[18];
-	loc[0] = base + 1;            loc[1] = base - 1;
-	loc[2] = base + DY;           loc[3] = base - DY;
-	loc[4] = base + 1 + DY;       loc[5] = base - 1 - DY;
-	loc[6] = base + 1 - DY;       loc[7] = base - 1 + DY;
-	loc[8] = base + 1 + DZ;       loc[9] = base - 1 - DZ;
-	loc[10] = base + 1 - DZ;      loc[11] = base - 1 + DZ;
-	loc[12] = base + DY + DZ;     loc[13] = base - DY - DZ;
-	loc[14] = base + DY - DZ;     loc[15] = base - DY + DZ;
-	loc[16] = base + DZ;          loc[17] = base - DZ;
+	if (beta_uses_offset_table<T, SMAG>()) {
 #pragma unroll
-	for (int i = 0; i < 18; i++) loc[i] += (long long)i * P.ns;
+		for (int i = 0; i < 18; i++) loc[i] = base + P.boff[i];
+	} else {
+		loc[0] = base + 1;            loc[1] = base - 1;
+		loc[2] = base + DY;           loc[3] = base - DY;
+		loc[4] = base + 1 + DY;       loc[5] = base - 1 - DY;
+		loc[6] = base + 1 - DY;       loc[7] = base - 1 + DY;
+		loc[8] = base + 1 + DZ;       loc[9] = base - 1 - DZ;
+		loc[10] = base + 1 - DZ;      loc[11] = base - 1 + DZ;
+		loc[12] = base + DY + DZ;     loc[13] = base - DY - DZ;
+		loc[14] = base + DY - DZ;     loc[15] = base - DY + DZ;
+		loc[16] = base + DZ;          loc[17] = base - DZ;
+#pragma unroll
+		for (int i = 0; i < 18; i++) loc[i] += (long long)i * P.ns;
+	}
 
 	T v[19][VEC];
 #pragma unroll
