@@ -270,6 +270,8 @@ def run_gpu(args):
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (n, n))
         n = world
     torch.cuda.set_device(local)
+    # the contract is ONE JSON line on stdout: NCCL's own banner (NCCL_DEBUG=VERSION/INFO) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -288,8 +290,11 @@ def run_gpu(args):
     # the library launches on torch-owned streams so that NCCL (torch.distributed) and a
     # CUDA-graph capture of the two-step cycle see the same stream order
     compute_stream, comm_stream = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
+    axis_order = args.axis_order
+    if axis_order == "auto":
+        axis_order = "zyx" if cfg.subdomain_num[0] > 1 else "xyz"
     mgr = CManager(domain, cfg.subdomain_num, backend=backend, device=local, config=cfg,
-                   sync_mode=args.sync if world > 1 else "host", dtype=np_dtype,
+                   sync_mode=args.sync if world > 1 else "host", dtype=np_dtype, axis_order=axis_order,
                    store_velocity=False, store_density=False,
                    compute_stream=compute_stream.cuda_stream, comm_stream=comm_stream.cuda_stream)
     mgr.initSimulation(rank)
@@ -451,7 +456,8 @@ def run_gpu(args):
                          "note": "per GPU; step kernels lbm_alpha_kernel/lbm_beta_kernel alternate; %d B per "
                                  "lattice-site update x cells per launch / CUDA-event time" % bytes_per_lup},
             "halo": halo,
-            "sync_mode": args.sync if world > 1 else None, "cuda_graph": graph is not None,
+            "sync_mode": args.sync if world > 1 else None, "axis_order": axis_order if world > 1 else None,
+            "cuda_graph": graph is not None,
             "kernel_config": s.config(),
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -484,6 +490,9 @@ def main():
                     help="halo transport for N > 1 (p2p: one-sided NVLink peer stores; overlap/device: NCCL)")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--axis-order", default="auto", choices=["auto", "xyz", "zyx"],
+                    help="phase order of the halo sync (p2p): xyz = the reference's; zyx = x faces exchanged after "
+                         "the interior kernel, no x shell; auto = zyx when the decomposition cuts x")
     ap.add_argument("--graph", action="store_true", help="capture the 2-step cycle in a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -170,7 +170,21 @@ int lbmCommConnectLocal(lbm_t h, int face_id, lbm_t peer, int peer_face_id); /* 
 int lbmCommBeginSync(lbm_t h, int sync_kind);           /* next sequence number of that sync kind */
 int lbmCommPush(lbm_t h, int sync_kind, int axis);      /* push my faces of one axis (comm stream) */
 int lbmCommPull(lbm_t h, int sync_kind, int axis);      /* wait + unpack my faces of one axis */
-int lbmCommSync(lbm_t h, int sync_kind);                /* begin; for axis x,y,z: push; pull */
+int lbmCommSync(lbm_t h, int sync_kind);                /* begin; for each axis in order: push; pull */
+/* Order of the three axis phases of a sync.  Any fixed order delivers the same halo (every face
+ * spans the full extent of the other two axes, so a later phase forwards the rims an earlier one
+ * received); only the leftovers in ghost cells nobody reads differ.
+ *   LBM_AXIS_ORDER_XYZ  the reference's CComm walk (src/CManager.hpp:122-199), the default;
+ *   LBM_AXIS_ORDER_ZYX  z, y, then x.  lbmCommStep then keeps the z and y faces under the
+ *                       interior kernel and exchanges the x faces AFTER it, unsplit: an x shell
+ *                       touches both ends of every row of the sub-domain (one DRAM page per
+ *                       row and slot) and costs half a step whatever its width, the exposed x
+ *                       exchange a few per cent -- use it when the decomposition cuts x.
+ * Every rank of a run must use the same order.  LBM_B200_AXIS_ORDER=xyz|zyx presets it. */
+#define LBM_AXIS_ORDER_XYZ 0
+#define LBM_AXIS_ORDER_ZYX 1
+int lbmCommSetAxisOrder(lbm_t h, int order);
+int lbmCommGetAxisOrder(lbm_t h, int *order);
 /* one overlapped time step: shell kernels -> (push/pull on the comm stream || interior kernel)
  * -> join; == CController::computeNextStep (src/CController.hpp:385-391) */
 int lbmCommStep(lbm_t h);

@@ -92,12 +92,15 @@ def _dot(a, b):
 class MultiDomain:
     """All ranks of a decomposed run inside one process (each rank = one solver object)."""
 
-    def __init__(self, domain_size, subdomain_nums, make_solver, slots="reference"):
+    def __init__(self, domain_size, subdomain_nums, make_solver, slots="reference", axis_order=(0, 1, 2)):
         self.domain_size = tuple(domain_size)
         self.nums = tuple(subdomain_nums)
         self.sub_size = decompose(domain_size, subdomain_nums)
         self.nranks = self.nums[0] * self.nums[1] * self.nums[2]
         self.slots = slots
+        # phase order of a sync: (0, 1, 2) is the reference's CComm walk (src/CManager.hpp:122-199);
+        # (2, 1, 0) is the product's LBM_AXIS_ORDER_ZYX option -- same halo, different leftovers in ghost cells
+        self.axis_order = tuple(axis_order)
         self.ranks = []
         for r in range(self.nranks):
             coords, bc, comms, origin = rank_layout(r, self.nums, self.sub_size)
@@ -109,7 +112,7 @@ class MultiDomain:
 
     def sync(self, beta):
         S = self.sub_size
-        for axis in range(3):
+        for axis in self.axis_order:
             staged = []
             for r, rk in enumerate(self.ranks):
                 for c in rk["comms"]:

@@ -23,6 +23,7 @@ def main():
     steps = int(os.environ["LBM_TEST_STEPS"])
     sync = os.environ["LBM_TEST_SYNC"]
     out = os.environ["LBM_TEST_OUT"]
+    axis_order = os.environ.get("LBM_TEST_AXIS_ORDER") or "xyz"     # the oracle run it is compared with
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
@@ -34,7 +35,7 @@ def main():
     compute_stream, comm_stream = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
     mgr = CManager(CDomain(-1, D, (0, 0, 0), (0.1, 0.1, 0.1)), nums, backend=TorchDistributedBackend(),
                    device=local, sync_mode=sync, config=cfg, dtype=np.float32,
-                   beta_order=capi.LBM_BETA_ORDER_LINEAR,
+                   beta_order=capi.LBM_BETA_ORDER_LINEAR, axis_order=axis_order,
                    compute_stream=compute_stream.cuda_stream, comm_stream=comm_stream.cuda_stream)
     mgr.initSimulation(rank)
     ctrl = mgr.getController()

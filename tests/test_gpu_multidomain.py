@@ -71,6 +71,43 @@ def test_decomposed_equals_single_domain(D, nums, steps, slots, transport, overl
         assert bits_equal(ctrl.getSolver().storeDensityDistribution(), md.ranks[r]["solver"].dd), (r, "dd vs oracle")
 
 
+@pytest.mark.parametrize("D,nums,steps", [
+    ((32, 16, 16), (2, 1, 1), 40),
+    ((36, 16, 16), (3, 1, 1), 41),
+    ((24, 24, 12), (2, 2, 1), 60),
+    ((24, 24, 24), (2, 2, 2), 81),
+    ((64, 32, 48), (2, 1, 3), 30),
+    ((16, 16, 24), (1, 1, 2), 31),       # no x neighbour: z,y,x order with nothing left to do after the interior
+])
+@pytest.mark.parametrize("overlap", [False, True])
+def test_zyx_axis_order_x_faces_after_the_interior(D, nums, steps, overlap):
+    """LBM_AXIS_ORDER_ZYX (include/lbm_b200.h): z and y faces under the interior kernel, x faces
+    exchanged after it without an x shell.  Same acceptance as the default order: the reference's
+    validate criterion against the single domain, plus every population of every sub-domain
+    (ghost layers included) against the oracle run with the same phase order."""
+    L = (0.1, 0.1, 0.1)
+    sim = InProcessSimulation(CDomain(-1, D, (0, 0, 0), L), nums, transport="p2p", overlap=overlap, config=_cfg(),
+                              dtype=np.float32, beta_order=capi.LBM_BETA_ORDER_LINEAR, axis_order="zyx")
+    assert all(c.getSolver().commAxisOrder() == capi.LBM_AXIS_ORDER_ZYX for c in sim.controllers)
+    sim.run(steps)
+    p = sim.controllers[0].getSolver().params
+    V = validation_domain_size(D, nums)
+    single = CLbmSolver(0, 0, [[1, 1]] * 3, CDomain(0, V, (0, 0, 0), L), dtype=np.float32, store_velocity=True,
+                        store_density=True, beta_order=capi.LBM_BETA_ORDER_LINEAR, params=p)
+    rect = (V[0] - 2, 1, V[2] - 2)
+    single.setFlags(np.full(rect[0] * rect[2], 4, np.int32), (1, V[1] - 2, 1), rect)
+    single.simulationSteps(steps)
+    inner = tuple(s - 2 for s in sim.sub_size)
+    make, po = omulti.make_oracle_factory(D, nums, L, dtype=np.float32, variant=1)
+    md = omulti.MultiDomain(D, nums, make, slots="minimal", axis_order=(2, 1, 0))
+    md.run(steps)
+    for r, ctrl in enumerate(sim.controllers):
+        o = validation_sub_origin(r, nums, inner)
+        s = ctrl.getSolver()
+        assert bits_equal(s.storeVelocity(origin=(1, 1, 1), size=inner), single.storeVelocity(origin=o, size=inner)), (r, "velocity")
+        assert bits_equal(s.storeDensityDistribution(), md.ranks[r]["solver"].dd), (r, "dd vs oracle")
+
+
 def _unused_comm_tables_match_the_oracle_restatement():
     from turbulent_lbm_multigpu_b200.controller import CManager
     D, nums = (24, 36, 48), (2, 3, 4)

@@ -39,19 +39,24 @@ def _free_port():
     ((32, 32, 48), (1, 1, 2), 20, "device"), ((32, 32, 48), (1, 1, 2), 21, "host"),
     ((96, 32, 32), (2, 1, 1), 20, "p2p"), ((96, 32, 32), (2, 1, 1), 21, "overlap"),
     ((32, 32, 64), (1, 2, 2), 15, "p2p"),
+    ((96, 32, 32), (2, 1, 1), 21, "p2p:zyx"),      # x faces exchanged after the interior kernel
+    ((64, 32, 64), (2, 1, 2), 15, "p2p:zyx"),
 ])
 def test_torchrun_ranks_equal_oracle(tmp_path, D, nums, steps, sync):
+    sync, _, axis_order = sync.partition(":")
     world = nums[0] * nums[1] * nums[2]
     if _gpus() < world:
         pytest.skip("needs %d GPUs" % world)
     env = dict(os.environ, LBM_TEST_DOMAIN=",".join(map(str, D)), LBM_TEST_NUMS=",".join(map(str, nums)),
-               LBM_TEST_STEPS=str(steps), LBM_TEST_SYNC=sync, LBM_TEST_OUT=str(tmp_path))
+               LBM_TEST_STEPS=str(steps), LBM_TEST_SYNC=sync, LBM_TEST_OUT=str(tmp_path),
+               LBM_TEST_AXIS_ORDER=axis_order)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "_gpu_rank_worker.py")]
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:]
     make, po = omulti.make_oracle_factory(D, nums, (0.1, 0.1, 0.1), dtype=np.float32, variant=1)
-    md = omulti.MultiDomain(D, nums, make, slots="reference" if sync == "host" else "minimal")
+    md = omulti.MultiDomain(D, nums, make, slots="reference" if sync == "host" else "minimal",
+                            axis_order=(2, 1, 0) if axis_order == "zyx" else (0, 1, 2))
     md.run(steps)
     for rank in range(world):
         z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))

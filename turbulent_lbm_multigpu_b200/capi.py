@@ -16,6 +16,7 @@ LBM_F32, LBM_F64 = 0, 1
 LBM_BETA_ORDER_SHIPPED, LBM_BETA_ORDER_LINEAR = 0, 1
 LBM_HALO_SLOTS_REFERENCE, LBM_HALO_SLOTS_MINIMAL = 0, 1
 LBM_SYNC_ALPHA, LBM_SYNC_BETA = 0, 1
+LBM_AXIS_ORDER_XYZ, LBM_AXIS_ORDER_ZYX = 0, 1
 LBM_BUF_DD, LBM_BUF_FLAGS, LBM_BUF_VELOCITY, LBM_BUF_DENSITY = 0, 1, 2, 3
 LBM_PROFILE_EVENTS, LBM_PROFILE_NVTX = 1, 2
 
@@ -86,6 +87,8 @@ SYMBOLS = {
     "lbmCommPush": (_i, [_vp, _i, _i]),
     "lbmCommPull": (_i, [_vp, _i, _i]),
     "lbmCommSync": (_i, [_vp, _i]),
+    "lbmCommSetAxisOrder": (_i, [_vp, _i]),
+    "lbmCommGetAxisOrder": (_i, [_vp, _ip]),
     "lbmCommStep": (_i, [_vp]),
     "lbmStepShell": (_i, [_vp, _i]),
     "lbmStepShellComm": (_i, [_vp, _i]),

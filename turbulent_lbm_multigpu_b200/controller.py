@@ -17,6 +17,8 @@ by the CUDA C ABI and the host-staged MPI exchange by three interchangeable sync
             kernel packs a face and stores it straight into the neighbour's staging block and
             raises a flag, the neighbour waits on the flag on the device and unpacks; the whole
             overlapped step is ONE call into the library (lbmCommStep) -- no NCCL, no host sync.
+            ``axis_order="zyx"`` exchanges the x faces after the interior kernel instead of
+            splitting an x shell off (include/lbm_b200.h, LBM_AXIS_ORDER_ZYX).
 """
 from __future__ import annotations
 
@@ -35,7 +37,7 @@ MPI_TAG_ALPHA_SYNC, MPI_TAG_BETA_SYNC = 0, 1
 class CController:
     def __init__(self, UID, domain: CDomain, BC, backend=None, device=0, sync_mode="host",
                  solver_factory=None, dtype=np.float32, slots=capi.LBM_HALO_SLOTS_MINIMAL,
-                 config=None, **solver_kw):
+                 config=None, axis_order=None, **solver_kw):
         self._UID = int(UID)
         self._domain = domain
         self._BC = [[int(BC[a][s]) for s in range(2)] for a in range(3)]
@@ -44,6 +46,9 @@ class CController:
         self.device = device
         self.sync_mode = sync_mode
         self.slots = slots
+        # p2p mode: "xyz" | "zyx"; None = z,y,x when the decomposition cuts x (decided in connectFaces),
+        # unless LBM_B200_AXIS_ORDER presets the library
+        self.axis_order = axis_order
         self.dtype = np.dtype(dtype)
         self.config = config or ConfigSingleton.Instance()
         self.vector_checksum = 0.0
@@ -74,6 +79,8 @@ class CController:
         if err is not None and callable(err) and err():
             print(self.cLbmPtr.error.getString())
             return -1
+        if self.axis_order is not None and hasattr(self.cLbmPtr, "commSetAxisOrder"):
+            self.cLbmPtr.commSetAxisOrder(self.axis_order)
         if hasattr(self.cLbmPtr, "wait"):
             self.cLbmPtr.wait()
         return 0
@@ -161,7 +168,12 @@ class CController:
     def connectFaces(self):
         """p2p mode: register every CComm as a face, exchange the CUDA-IPC handles of the receive
         blocks with the neighbours (torch.distributed object gather) and map them."""
+        import os
         s = self.cLbmPtr
+        if self.axis_order is None and not os.environ.get("LBM_B200_AXIS_ORDER") \
+                and any(c.axis == 0 for c in self._comm_container):
+            # every rank of an x-cutting decomposition has an x neighbour, so all ranks agree
+            s.commSetAxisOrder(capi.LBM_AXIS_ORDER_ZYX)
         self._face_ids = [s.commAddFace(c, self.slots) for c in self._comm_container]
         mine = {}
         for c, fid in zip(self._comm_container, self._face_ids):
@@ -434,14 +446,18 @@ class InProcessSimulation:
                 pid = ids[(c.getDstId(), ctrl.getUid(), c.axis, -d)]
                 s.commConnectLocal(fid, self.controllers[c.getDstId()].getSolver(), pid)
 
-    def _sync_p2p(self, beta):
+    def _sync_p2p(self, beta, x_after_interior=False):
         """Every push of an axis is enqueued before any wait of that axis, so the device-side
         flag waits can never be ordered ahead of the push they wait for."""
         kind = capi.LBM_SYNC_BETA if beta else capi.LBM_SYNC_ALPHA
         solvers = [c.getSolver() for c in self.controllers]
         for s in solvers:
             s.commBeginSync(kind)
-        for axis in range(3):
+        zyx = solvers[0].commAxisOrder() == capi.LBM_AXIS_ORDER_ZYX
+        for axis in ((2, 1, 0) if zyx else (0, 1, 2)):
+            if axis == 0 and x_after_interior:      # lbmCommStep's z,y,x order: x faces follow the interior
+                for s in solvers:
+                    s.commWaitCompute()
             for s in solvers:
                 s.commPush(kind, axis)
             for s in solvers:
@@ -474,16 +490,18 @@ class InProcessSimulation:
         solvers = [c.getSolver() for c in self.controllers]
         if self.transport == "p2p":
             beta_step = (solvers[0].simulation_step_counter & 1) == 0
+            zyx = solvers[0].commAxisOrder() == capi.LBM_AXIS_ORDER_ZYX
             if self.overlap:
                 for ctrl, s in zip(self.controllers, solvers):
+                    split = ctrl.ghost_faces() & (~3 if zyx else ~0)     # z,y,x: no x shell
                     s.commWaitCompute()
-                    s.stepShellComm(ctrl.ghost_faces())
-                    s.stepInterior(ctrl.ghost_faces())
+                    s.stepShellComm(split)
+                    s.stepInterior(split)
             else:
                 for s in solvers:
                     s.simulationStep()
                     s.commWaitCompute()
-            self._sync_p2p(beta=beta_step)
+            self._sync_p2p(beta=beta_step, x_after_interior=self.overlap and zyx)
             for s in solvers:
                 s.computeWaitComm()
             return

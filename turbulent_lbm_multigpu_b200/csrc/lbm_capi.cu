@@ -44,6 +44,7 @@ struct lbm_solver {
 	lbm_desc desc;
 	std::vector<lbm_face> faces;
 	unsigned int sync_seq[2];
+	int axis_order;              /* LBM_AXIS_ORDER_*: phase order of a sync */
 	int device;
 	int dtype;
 	int sx, sy, sz;
@@ -471,6 +472,8 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	h->xshell = 32;
 	if (const char *e = getenv("LBM_B200_XSHELL")) h->xshell = atoi(e) > 1 ? atoi(e) : 2;
 	h->sync_seq[0] = h->sync_seq[1] = 0;
+	h->axis_order = LBM_AXIS_ORDER_XYZ;
+	if (const char *e = getenv("LBM_B200_AXIS_ORDER")) if (!strcmp(e, "zyx") || !strcmp(e, "ZYX")) h->axis_order = LBM_AXIS_ORDER_ZYX;
 	h->smag = d->smagorinsky_cs != 0.0;
 	h->u_lid = d->u_lid;
 	const int maxvec = d->dtype == LBM_F32 ? 4 : 2;
@@ -1123,13 +1126,30 @@ int lbmCommPull(lbm_t h, int sync_kind, int axis)
 	return axis_pull(h, sync_kind, axis, h->comm);
 }
 
+int lbmCommSetAxisOrder(lbm_t h, int order)
+{
+	CHECK_HANDLE(h);
+	if (order != LBM_AXIS_ORDER_XYZ && order != LBM_AXIS_ORDER_ZYX) return fail(h, LBM_ERR_INVALID, "unknown axis order");
+	h->axis_order = order;
+	return LBM_OK;
+}
+
+int lbmCommGetAxisOrder(lbm_t h, int *order)
+{
+	CHECK_HANDLE(h);
+	if (!order) return fail(h, LBM_ERR_INVALID, "null order");
+	*order = h->axis_order;
+	return LBM_OK;
+}
+
 int lbmCommSync(lbm_t h, int sync_kind)
 {
 	CHECK_HANDLE(h);
 	if (int rc = lbmCommBeginSync(h, sync_kind)) return rc;
-	/* x, then y, then z: later axes carry the rims the earlier ones delivered
-	 * (the reference's sequential CComm walk, src/CManager.hpp:122-199) */
-	for (int axis = 0; axis < 3; axis++) {
+	/* one axis after the other: later axes carry the rims the earlier ones delivered
+	 * (x, y, z = the reference's sequential CComm walk, src/CManager.hpp:122-199) */
+	for (int i = 0; i < 3; i++) {
+		const int axis = h->axis_order == LBM_AXIS_ORDER_ZYX ? 2 - i : i;
 		if (int rc = lbmCommPush(h, sync_kind, axis)) return rc;
 		if (int rc = lbmCommPull(h, sync_kind, axis)) return rc;
 	}
@@ -1140,6 +1160,9 @@ static int comm_step(lbm_t h, cudaEvent_t *marks /* NULL or 5 timing events */)
 {
 	if (int rc = use_device(h)) return rc;
 	const int faces = ghost_mask_of_faces(h);
+	/* z,y,x order: x faces are not split off; they are exchanged after the interior kernel */
+	const bool x_last = h->axis_order == LBM_AXIS_ORDER_ZYX && (faces & 3) != 0;
+	const int split = x_last ? (faces & ~3) : faces;
 	const int kind = (h->counter & 1) ? LBM_SYNC_ALPHA : LBM_SYNC_BETA;   /* the sync that follows this step */
 	/* fork: the (high-priority) comm stream runs shell -> push -> wait -> unpack while the
 	 * compute stream runs the interior kernel; shell and interior touch disjoint
@@ -1147,14 +1170,26 @@ static int comm_step(lbm_t h, cudaEvent_t *marks /* NULL or 5 timing events */)
 	 * enqueued first so that its few blocks are scheduled ahead of the interior's. */
 	if (marks) CUDA_TRY(h, cudaEventRecord(marks[0], h->compute));
 	if (int rc = lbmStreamWaitStream(h, 1)) return rc;
-	if (int rc = lbmStepShellComm(h, faces)) return rc;
+	if (int rc = lbmStepShellComm(h, split)) return rc;
 	if (marks) CUDA_TRY(h, cudaEventRecord(marks[1], h->comm));
 	h->step_aux = h->comm;                                  /* the comm stream is forked: wrapping kernel there */
-	int rc_int = lbmStepInterior(h, faces);
+	int rc_int = lbmStepInterior(h, split);
 	h->step_aux = NULL;
 	if (rc_int) return rc_int;
 	if (marks) CUDA_TRY(h, cudaEventRecord(marks[2], h->compute));
-	if (int rc = lbmCommSync(h, kind)) return rc;
+	if (!x_last) {
+		if (int rc = lbmCommSync(h, kind)) return rc;
+	} else {
+		if (int rc = lbmCommBeginSync(h, kind)) return rc;
+		for (int axis = 2; axis >= 1; axis--) {             /* hidden under the interior kernel */
+			if (int rc = lbmCommPush(h, kind, axis)) return rc;
+			if (int rc = lbmCommPull(h, kind, axis)) return rc;
+		}
+		/* the x faces hold cells the interior kernel updates: the comm stream picks up behind it */
+		if (int rc = lbmStreamWaitStream(h, 1)) return rc;
+		if (int rc = lbmCommPush(h, kind, 0)) return rc;
+		if (int rc = lbmCommPull(h, kind, 0)) return rc;
+	}
 	if (marks) CUDA_TRY(h, cudaEventRecord(marks[3], h->comm));
 	if (int rc = lbmStreamWaitStream(h, 0)) return rc;     /* join: the next step needs the halo */
 	if (marks) CUDA_TRY(h, cudaEventRecord(marks[4], h->compute));

@@ -113,6 +113,14 @@ class CController {
 			_face_ids.push_back(fid);
 			_world->publishFace(_UID, c->getDstId(), c->axis(), dir[c->axis()], fid);
 		}
+		/* a decomposition that cuts x (then every rank has an x neighbour): z, y, x phase order --
+		 * x faces after the interior kernel instead of an x shell (include/lbm_b200.h) */
+		if (axis_order >= 0) check(lbmCommSetAxisOrder(h, axis_order));
+		else if (!getenv("LBM_B200_AXIS_ORDER")) {
+			bool cuts_x = false;
+			for (size_t i = 0; i < _comm_container.size(); i++) cuts_x |= _comm_container[i]->axis() == 0;
+			if (cuts_x) check(lbmCommSetAxisOrder(h, LBM_AXIS_ORDER_ZYX));
+		}
 		_world->barrier();
 		for (size_t i = 0; i < _comm_container.size(); i++) {
 			CComm<T> *c = _comm_container[i];
@@ -192,12 +200,13 @@ public:
 	double seconds, mlups;          /* filled by run() */
 	CProfiler profiler;             /* per rank (the reference's ProfilerSingleton is per MPI process) */
 	int halo_slots;                 /* LBM_HALO_SLOTS_MINIMAL (5 per face) | _REFERENCE (19) */
+	int axis_order;                 /* LBM_AXIS_ORDER_*; -1 (default): z,y,x when the decomposition cuts x */
 	int beta_order;
 
 	CController(int UID, CDomain<T> domain, int BC[3][2], CRankWorld *world = NULL, LbmSyncMode sync = SYNC_AUTO,
 			int p_beta_order = LBM_BETA_ORDER_SHIPPED)
 		: _UID(UID), _domain(domain), cLbmPtr(NULL), _world(world), _sync(sync), _connected(false),
-		  vector_checksum(0), seconds(0), mlups(0), halo_slots(LBM_HALO_SLOTS_MINIMAL), beta_order(p_beta_order)
+		  vector_checksum(0), seconds(0), mlups(0), halo_slots(LBM_HALO_SLOTS_MINIMAL), axis_order(-1), beta_order(p_beta_order)
 	{
 		for (int a = 0; a < 3; a++) for (int s = 0; s < 2; s++) _BC[a][s] = BC[a][s];
 		if (initLBMSolver() == -1) {

@@ -283,6 +283,18 @@ class CLbmSolver:
     def commSync(self, kind):
         self._ck(self._lib.lbmCommSync(self._h, int(kind)))
 
+    def commSetAxisOrder(self, order):
+        """LBM_AXIS_ORDER_XYZ (the reference's CComm walk) or LBM_AXIS_ORDER_ZYX (x faces exchanged
+        after the interior kernel, unsplit); accepts the constants or "xyz" / "zyx"."""
+        if isinstance(order, str):
+            order = {"xyz": capi.LBM_AXIS_ORDER_XYZ, "zyx": capi.LBM_AXIS_ORDER_ZYX}[order.lower()]
+        self._ck(self._lib.lbmCommSetAxisOrder(self._h, int(order)))
+
+    def commAxisOrder(self):
+        o = ctypes.c_int()
+        self._ck(self._lib.lbmCommGetAxisOrder(self._h, ctypes.byref(o)))
+        return o.value
+
     def commStep(self):
         self._ck(self._lib.lbmCommStep(self._h))
 
