@@ -218,6 +218,9 @@ def reference_sample_size(steps, warmup, threads, limit_s=150.0):
     return 64
 
 
+RESULT_OUT = sys.stdout     # main() swaps in a private copy of the original stdout
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -237,7 +240,7 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
     return 0
 
 
@@ -270,8 +273,6 @@ def run_gpu(args):
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (n, n))
         n = world
     torch.cuda.set_device(local)
-    # the contract is ONE JSON line on stdout: NCCL's own banner (NCCL_DEBUG=VERSION/INFO) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -468,7 +469,7 @@ def run_gpu(args):
             except Exception as e:    # the checker being absent must not hide the GPU result
                 line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": os.cpu_count(), "kind": "reference",
                                         "sample": "unavailable: %s" % e}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -495,6 +496,13 @@ def main():
                          "the interior kernel, no x shell; auto = zyx when the decomposition cuts x")
     ap.add_argument("--graph", action="store_true", help="capture the 2-step cycle in a CUDA graph")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, OpenMP/torch warnings): keep the real stdout for the result line and
+    # point file descriptor 1 at stderr for everything else.
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)
