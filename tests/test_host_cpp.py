@@ -125,7 +125,7 @@ def test_cpp_sample_conf_parses(exe):
 @pytest.mark.gpu
 @pytest.mark.parametrize("D,nums,loops", [((96, 32, 32), (3, 1, 1), 40), ((16, 16, 24), (1, 1, 2), 41),
                                           ((24, 24, 24), (2, 2, 2), 30)])
-@pytest.mark.parametrize("sync", ["copy", "host", "auto"])
+@pytest.mark.parametrize("sync", ["copy", "host", "auto", "p2p"])     # p2p: one-sided exchange, z,y,x order when x is cut
 def test_cpp_validate_mode(exe, tmp_path, D, nums, loops, sync):
     """the reference's own acceptance test (src/main.cpp:309-408): 0 failed cells at 1e-15"""
     args = ["-c", write_conf(tmp_path / "c.xml", D, nums, loops=loops, validate=1)]
