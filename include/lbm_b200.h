@@ -160,7 +160,12 @@ int lbmHaloCopyPeer(lbm_t src, const int src_origin[3], lbm_t dst, const int dst
  * ([flag words][alpha staging][beta staging]); the neighbour maps it (same process: directly;
  * other process: CUDA IPC) and its push kernel packs the face and stores it straight into
  * that block over NVLink, then raises the block's flag word; the owner's pull waits on the
- * flag (device side) and unpacks.  Replaces syncAlpha/syncBeta (src/CController.hpp:265-383). */
+ * flag (device side) and unpacks.  Replaces syncAlpha/syncBeta (src/CController.hpp:265-383).
+ * Meant for one rank per GPU.  Several ranks MAY share a GPU (tests do), but a pull kernel spins
+ * until the neighbour's push has run, so all streams of the ranks on one device (two per rank) must
+ * be able to make progress independently: keep them within the device's hardware queues
+ * (CUDA_DEVICE_MAX_CONNECTIONS, default 8 -> at most 4 free-running ranks per GPU), or enqueue every
+ * push of an axis before any pull of that axis from one host thread (lbmCommPush / lbmCommPull). */
 int lbmCommAddFace(lbm_t h, int dst_rank, const int send_origin[3], const int recv_origin[3],
 		const int size[3], const int dir[3], int slots, int *face_id);
 int lbmCommFaceCount(lbm_t h, int *count);
