@@ -477,8 +477,9 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	h->smag = d->smagorinsky_cs != 0.0;
 	h->u_lid = d->u_lid;
 	const int maxvec = d->dtype == LBM_F32 ? 4 : 2;
-	/* default: 2 cells per thread (measured best on B200 for fp32: 96 registers -> 20 resident
-	 * warps per SM, profiles/r1_sweep_launch_config.md); 4 is available on request */
+	/* default: 2 cells per thread (measured best on B200 for fp32: 80-96 registers -> 20-24
+	 * resident warps per SM, profiles/r1_sweep_launch_config_f32.jsonl, r1_summary.md); 4 is
+	 * available on request */
 	int vec = d->vector_width > 0 ? d->vector_width : 2;
 	if (vec > maxvec) vec = maxvec;
 	while (vec > 1 && (h->sx % vec) != 0) vec >>= 1;
