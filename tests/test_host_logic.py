@@ -220,3 +220,24 @@ def test_debug_dumps_follow_the_reference_format(tmp_path, tname, dtype):
     # slot 5 starts at element 60: row labels count from the array start (60 // 16 = 3 appears at element 64)
     assert lines[i + 1].count(" ") == 4 and not lines[i + 1].startswith("3: ")
     assert lines[i + 2].startswith("4: ") and "" in lines[i + 1:i + 8]
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header compiles as strict C99 and a C program (no C++,
+    no Python, no torch) links against liblbm_b200.so and drives it.  Without a GPU creation fails
+    loudly with LBM_ERR_NO_DEVICE; with one the program steps a small solver."""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", "abi_from_c.c")
+    exe = str(tmp_path / "abi_from_c")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", src, "-o", exe,
+                           "-L" + libdir, "-llbm_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe], text=True, timeout=120)
+    lines = dict(l.split(" ", 1) for l in out.strip().split("\n"))
+    assert lines["version"] == "100"
+    assert lines["mask"].startswith("rc=0 0x") and bin(int(lines["mask"].split("0x")[1], 16)).count("1") == 5
+    if lines["create"].startswith("rc=0"):
+        assert lines["stepped"] == "rc=0 counter=2" and lines["destroy"] == "rc=0"
+    else:
+        assert lines["create"] == "rc=3 handle=no" and "no CPU fallback" in lines["error:"]
+        assert lines["null-handle"] == "step rc=%d" % 1       # LBM_ERR_INVALID
