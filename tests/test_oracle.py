@@ -188,6 +188,32 @@ def test_port_equals_reference_kernels_step_by_step(size, dtype, variant, bc, st
 
 
 @needs_ref
+@pytest.mark.parametrize("dtype,variant", [(np.float32, 0), (np.float32, 1), (np.float64, 0)])
+def test_port_equals_reference_kernels_with_obstacles_inside(dtype, variant):
+    """An obstacle block, scattered obstacle cells, ghost cells inside the domain and a few
+    velocity-injection cells away from the lid plane: every flag branch of both kernels
+    (lbm_alpha.cl:177-343, lbm_beta.cl:495-656) next to fluid, bit for bit against the reference."""
+    from turbulent_lbm_multigpu_b200.skeleton import compute_parameters
+    size = (40, 24, 16)
+    p = compute_parameters(size, (0.1,) * 3, dtype=dtype)
+    a = ref.RefSolver(size, [1, 8, 1, 1, 8, 1], p.inv_tau, p.gravitation, p.u_lid, dtype=dtype, variant=variant)
+    b = port.OracleSolver(size, [1, 8, 1, 1, 8, 1], p.inv_tau, p.gravitation, p.u_lid, dtype=dtype, variant=variant)
+    rng = np.random.default_rng(11)
+    speckle = np.where(rng.random(10 * 8 * 6) < 0.15, 1, 2).astype(np.int32)
+    for s in (a, b):
+        set_lid(s, size)
+        s.setFlags(np.ones(6 * 5 * 4, np.int32), (9, 7, 5), (6, 5, 4))
+        s.setFlags(speckle, (24, 4, 3), (10, 8, 6))
+        s.setFlags(np.full(3, 4, np.int32), (20, 10, 8), (3, 1, 1))
+        s.setFlags(np.full(4, 8, np.int32), (30, 15, 10), (2, 2, 1))
+    for i in range(14):
+        a.simulationStep()
+        b.simulationStep()
+        for name in ("dd", "velocity", "density", "flags"):
+            assert bits_equal(getattr(a, name), getattr(b, name)), (variant, i, name)
+
+
+@needs_ref
 def test_reference_rect_kernels_equal_port_slicing():
     from turbulent_lbm_multigpu_b200.skeleton import compute_parameters
     size = (24, 20, 12)
