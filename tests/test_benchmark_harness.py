@@ -45,3 +45,28 @@ def test_ini_averaging(tmp_path):
     assert res[1]["MLUPS"] == 105.0 and res[2]["MLUPS"] == 195.0 and res[2]["NUM_EXP"] == 2
     assert abs(res[2]["SPEEDUP"] - 195.0 / 105.0) < 1e-12 and abs(res[2]["EFFICIENCY"] - 195.0 / 210.0) < 1e-12
     assert abs(res[1]["ROOFLINE_FRAC_PER_GPU"] - 105.0 * 156.0 / 1e3 / 1000.0) < 1e-12
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's contract: ONE JSON line on stdout (libraries that print there are redirected to
+    stderr), the reference arm's extra keys, and -- under torchrun with N > 1 -- ranks other than 0
+    exit 0 without work or output.  The reference arm runs on the host cores, so this is a CPU test."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--size", "32"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-1500:]
+    lines = p.stdout.strip().split("\n")
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "MLUPS" and j["unit"] == "MLUPS" and j["higher_is_better"] is True
+    assert j["steps"] == 1 and j["value"] > 0 and j["n_gpus"] == 1 and j["gpu_launches"] == 0
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
+    assert j["cpu_baseline"]["value"] == j["value"] and "sample" in j["cpu_baseline"]
+    assert j["e2e"] == {"value": j["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in j["config"] and "model" not in j["config"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0 and p.stdout == ""
