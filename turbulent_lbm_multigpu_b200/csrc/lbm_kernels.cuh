@@ -546,10 +546,13 @@ __device__ __forceinline__ bool beta_block_is_general(const StepParams<T> &P)
 #ifndef LBM_BETA_OFFTAB
 #define LBM_BETA_OFFTAB 2
 #endif
-template <typename T, bool SMAG>
+template <typename T, bool SMAG, bool STORE>
 __device__ __forceinline__ constexpr bool beta_uses_offset_table()
 {
-	return LBM_BETA_OFFTAB == 1 || (LBM_BETA_OFFTAB == 2 && SMAG && sizeof(T) == 4);
+	/* fp32 Smagorinsky without output stores: 92 -> 80 registers, +5.6 % (measured).  With output
+	 * stores the table costs registers (95 -> 127), fp32 BGK likewise (96 -> 114, -4.5 % measured),
+	 * fp64 stays at 3 resident blocks either way (+-0 measured): arithmetic there. */
+	return LBM_BETA_OFFTAB == 1 || (LBM_BETA_OFFTAB == 2 && SMAG && !STORE && sizeof(T) == 4);
 }
 
 template <typename T, int VEC, bool SMAG, bool STORE, int ORDER>
@@ -566,7 +569,7 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	/* location (slot j, cell c + e_j) is read as d[j^1] and written as d[j] */
 	T *base = P.dd + gid;
 	T *loc[18];
-	if (beta_uses_offset_table<T, SMAG>()) {
+	if (beta_uses_offset_table<T, SMAG, STORE>()) {
 #pragma unroll
 		for (int i = 0; i < 18; i++) loc[i] = base + P.boff[i];
 	} else {
