@@ -1,5 +1,8 @@
-"""Worker for tests/test_gpu_multiprocess.py: one process per GPU under torchrun (NCCL rendezvous),
-the product's CManager/CController with the CUDA solver and the selected halo transport."""
+"""Worker for tests/test_gpu_multiprocess.py: one process per sub-domain under torchrun, the product's
+CManager/CController with the CUDA solver and the selected halo transport.  One rank per GPU when the
+box has enough of them (NCCL + gloo rendezvous); otherwise the ranks share the GPUs round robin and
+rendezvous over gloo only (NCCL refuses two ranks on one device) -- the p2p (CUDA IPC) and host
+transports do not need NCCL, so the multi-process path is exercised on a single-GPU box too."""
 import os
 import sys
 
@@ -24,18 +27,30 @@ def main():
     sync = os.environ["LBM_TEST_SYNC"]
     out = os.environ["LBM_TEST_OUT"]
     axis_order = os.environ.get("LBM_TEST_AXIS_ORDER") or "xyz"     # the oracle run it is compared with
+    order = {"linear": capi.LBM_BETA_ORDER_LINEAR, "shipped": capi.LBM_BETA_ORDER_SHIPPED}[
+        os.environ.get("LBM_TEST_BETA_ORDER") or "linear"]
+    cs = float(os.environ.get("LBM_TEST_CS") or 0.0)
+    dtype = np.float64 if os.environ.get("LBM_TEST_DTYPE") == "f64" else np.float32
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ndev = torch.cuda.device_count()
+    shared = world > ndev
+    local = local % ndev
     torch.cuda.set_device(local)
-    dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
+    if shared:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
     rank = dist.get_rank()
     cfg = CConfiguration()
     cfg.loops = steps
     cfg.domain_size, cfg.subdomain_num = D, nums
     cfg.debug_mode = True                      # STORE_VELOCITY / STORE_DENSITY
+    cfg.smagorinsky_constant = cs
     compute_stream, comm_stream = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
     mgr = CManager(CDomain(-1, D, (0, 0, 0), (0.1, 0.1, 0.1)), nums, backend=TorchDistributedBackend(),
-                   device=local, sync_mode=sync, config=cfg, dtype=np.float32,
-                   beta_order=capi.LBM_BETA_ORDER_LINEAR, axis_order=axis_order,
+                   device=local, sync_mode=sync, config=cfg, dtype=dtype,
+                   beta_order=order, axis_order=axis_order,
                    compute_stream=compute_stream.cuda_stream, comm_stream=comm_stream.cuda_stream)
     mgr.initSimulation(rank)
     ctrl = mgr.getController()

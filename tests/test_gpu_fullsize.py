@@ -13,7 +13,7 @@ it can).  Every property is bit-exact:
 import numpy as np
 import pytest
 
-from helpers import bits_equal, make_cuda
+from helpers import bits_equal, make_cuda, make_oracle, params_for, set_lid
 from turbulent_lbm_multigpu_b200 import capi
 from turbulent_lbm_multigpu_b200.configuration import CConfiguration
 from turbulent_lbm_multigpu_b200.controller import (InProcessSimulation, validation_domain_size,
@@ -22,6 +22,48 @@ from turbulent_lbm_multigpu_b200.domain import CDomain
 from turbulent_lbm_multigpu_b200.solver import CLbmSolver
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("size,dtype,cs,steps", [
+    ((256, 256, 256), np.float32, 0.0, 6),      # BASELINE configs[1] as the reference runs it (BGK)
+    ((256, 256, 256), np.float32, 0.1, 6),      # ... and as bench.py runs it (Smagorinsky C_s = 0.1)
+    ((192, 96, 96), np.float64, 0.0, 6),        # fp64 production kernels (no work-group quirk: 128 % 192 != 0)
+    ((192, 96, 96), np.float64, 0.1, 6),
+    ((384, 384, 16), np.float64, 0.1, 4),       # row length / plane size of configs[4]
+])
+def test_production_kernels_equal_oracle_and_reference_at_full_size(size, dtype, cs, steps):
+    """The DEFAULT launch configuration (what bench.py times: 2 cells per thread, 128-thread
+    blocks, shipped summation order, concurrent wrapping kernel) against the CPU oracle and --
+    for BGK, which is all the reference has -- against the reference's own kernels (oracle/_ref,
+    strict IEEE build, shipped shared-memory beta path).  Every population and every flag of
+    every cell, bit for bit, after each of the first steps."""
+    from oracle import ref
+    c = make_cuda(size, dtype, cs=cs, store=False)
+    cfgd = c.config()
+    assert cfgd["vector_width"] == 2 and cfgd["block_size"] == 128 and cfgd["wg_quirk"] == 0
+    o = make_oracle(size, dtype, cs=cs)
+    r = None
+    if cs == 0.0 and ref.available():
+        p = params_for(size, dtype)
+        try:
+            r = ref.RefSolver(size, [1] * 6, p.inv_tau, p.gravitation, p.u_lid, dtype=dtype, variant=ref.SHM)
+            set_lid(r, size)
+        except KeyError:
+            r = None
+    if cs == 0.0 and size[0] != 384:
+        assert r is not None, "oracle/_ref has no instance for %s %s" % (size, np.dtype(dtype).name)
+    for i in range(steps):
+        c.simulationStep()
+        o.simulationStep()
+        got = c.storeDensityDistribution()
+        assert bits_equal(got, o.dd), ("oracle", i)
+        if r is not None:
+            r.simulationStep()
+            assert bits_equal(got, r.dd), ("reference kernels", i)
+    assert bits_equal(c.storeFlags(), o.flags)
+    if r is not None:
+        assert bits_equal(c.storeFlags(), r.flags)
+    c.close()
 
 
 @pytest.mark.parametrize("size,dtype,cs,steps", [

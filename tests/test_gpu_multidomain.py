@@ -108,19 +108,48 @@ def test_zyx_axis_order_x_faces_after_the_interior(D, nums, steps, overlap):
         assert bits_equal(s.storeDensityDistribution(), md.ranks[r]["solver"].dd), (r, "dd vs oracle")
 
 
-def _unused_comm_tables_match_the_oracle_restatement():
-    from turbulent_lbm_multigpu_b200.controller import CManager
-    D, nums = (24, 36, 48), (2, 3, 4)
-    m = CManager.__new__(CManager)
-    m._domain = CDomain(-1, D, (0, 0, 0), (0.1,) * 3)
-    m._controller_kw = {}
-    m.setSubdomainNums(nums)
-    sub = omulti.decompose(D, nums)
-    for r in range(24):
-        rid, coords, BC, comms, origin = m.layout(r)
-        ocoords, obc, ocomms, oorigin = omulti.rank_layout(r, nums, sub)
-        assert coords == ocoords and BC == obc and origin == oorigin
-        assert [c.as_tuple() for c in comms] == [c.as_tuple() for c in ocomms]
+@pytest.mark.parametrize("D,nums,steps", [
+    ((40, 24, 32), (1, 1, 2), 31),       # z-slabs: what bench.py / the driver's scaling run uses
+    ((40, 24, 48), (1, 1, 3), 30),       # a rank with two faces
+    ((48, 40, 24), (2, 2, 2), 41),       # blocks (x cut: z,y,x order chosen like bench.py does)
+    ((80, 24, 16), (2, 1, 1), 30),       # the reference's x split
+])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("cs", [0.0, 0.1])
+def test_bench_defaults_decomposed_equal_oracle(D, nums, steps, dtype, cs):
+    """The configuration bench.py and the driver's scaling run actually use -- SHIPPED summation
+    order, Smagorinsky C_s = 0.1 (and BGK), fp32 and fp64, p2p transport with the overlapped step,
+    production (vectorised) kernels: sub-domain rows are no divisor of 128, so the work-group quirk
+    is off -- against the oracle's decomposed run with the same options, every population of every
+    rank, plus the reference's validate criterion against the single domain."""
+    L = (0.1, 0.1, 0.1)
+    cfg = _cfg()
+    cfg.smagorinsky_constant = cs
+    zyx = nums[0] > 1
+    sim = InProcessSimulation(CDomain(-1, D, (0, 0, 0), L), nums, transport="p2p", overlap=True, config=cfg,
+                              dtype=dtype, axis_order="zyx" if zyx else "xyz")
+    for c in sim.controllers:
+        k = c.getSolver().config()
+        assert k["wg_quirk"] == 0 and k["vector_width"] == 2
+    sim.run(steps)
+    make, po = omulti.make_oracle_factory(D, nums, L, dtype=dtype, variant=0, smagorinsky_cs=cs)
+    md = omulti.MultiDomain(D, nums, make, slots="minimal", axis_order=(2, 1, 0) if zyx else (0, 1, 2))
+    md.run(steps)
+    for r, ctrl in enumerate(sim.controllers):
+        assert bits_equal(ctrl.getSolver().storeDensityDistribution(), md.ranks[r]["solver"].dd), (r, "dd vs oracle")
+        assert bits_equal(ctrl.getSolver().storeFlags(), md.ranks[r]["solver"].flags), (r, "flags vs oracle")
+    p = sim.controllers[0].getSolver().params
+    V = validation_domain_size(D, nums)
+    single = CLbmSolver(0, 0, [[1, 1]] * 3, CDomain(0, V, (0, 0, 0), L), dtype=dtype, store_velocity=True,
+                        store_density=True, smagorinsky_cs=cs, params=p)
+    rect = (V[0] - 2, 1, V[2] - 2)
+    single.setFlags(np.full(rect[0] * rect[2], 4, np.int32), (1, V[1] - 2, 1), rect)
+    single.simulationSteps(steps)
+    inner = tuple(s - 2 for s in sim.sub_size)
+    for r, ctrl in enumerate(sim.controllers):
+        o = validation_sub_origin(r, nums, inner)
+        s = ctrl.getSolver()
+        assert bits_equal(s.storeVelocity(origin=(1, 1, 1), size=inner), single.storeVelocity(origin=o, size=inner)), (r, "velocity")
 
 
 def _device_count():
