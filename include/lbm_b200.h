@@ -34,7 +34,8 @@ extern "C" {
 #define LBM_ERR_INVALID        1   /* bad argument */
 #define LBM_ERR_CUDA           2   /* CUDA runtime failure (message has the CUDA error) */
 #define LBM_ERR_NO_DEVICE      3   /* no CUDA device: the product has no CPU fallback */
-#define LBM_ERR_UNSTABLE       4   /* tau outside [0.51, 2.5] (src/CLbmSkeleton.hpp:108-112) */
+#define LBM_ERR_TIMEOUT        4   /* a device-side halo wait gave up: the neighbour never pushed its face
+                                      (reported by lbmWait; LBM_B200_WAIT_TIMEOUT_MS, default 30000) */
 
 /* cell flags, src/common.h:19-22 */
 #define LBM_FLAG_OBSTACLE            (1 << 0)
@@ -172,19 +173,29 @@ int lbmCommFaceCount(lbm_t h, int *count);
 int lbmCommGetIpcHandle(lbm_t h, int face_id, void *handle64);            /* 64-byte cudaIpcMemHandle_t */
 int lbmCommConnectIpc(lbm_t h, int face_id, const void *peer_handle64);   /* peer in another process */
 int lbmCommConnectLocal(lbm_t h, int face_id, lbm_t peer, int peer_face_id); /* peer in this process */
-int lbmCommBeginSync(lbm_t h, int sync_kind);           /* next sequence number of that sync kind */
+/* Sequence numbers: every push of a face counts up a device-resident word and publishes it in the
+ * neighbour's flag; every pull counts up its own word and waits for the flag to reach it.  Nothing about
+ * them lives on the host or in kernel arguments, so a CUDA graph captured around lbmCommStep (or around
+ * push/pull calls) can be replayed any number of times and keeps synchronising.  Each face must see
+ * exactly one push and one pull per sync kind and step, in step order -- lbmCommSync / lbmCommStep do. */
+int lbmCommBeginSync(lbm_t h, int sync_kind);           /* kept for source compatibility: validates sync_kind, nothing else */
 int lbmCommPush(lbm_t h, int sync_kind, int axis);      /* push my faces of one axis (comm stream) */
-int lbmCommPull(lbm_t h, int sync_kind, int axis);      /* wait + unpack my faces of one axis */
-int lbmCommSync(lbm_t h, int sync_kind);                /* begin; for each axis in order: push; pull */
+int lbmCommPull(lbm_t h, int sync_kind, int axis);      /* wait (one device thread per face) + unpack my faces of one axis */
+int lbmCommSync(lbm_t h, int sync_kind);                /* for each axis in order: push; pull */
 /* Order of the three axis phases of a sync.  Any fixed order delivers the same halo (every face
  * spans the full extent of the other two axes, so a later phase forwards the rims an earlier one
  * received); only the leftovers in ghost cells nobody reads differ.
  *   LBM_AXIS_ORDER_XYZ  the reference's CComm walk (src/CManager.hpp:122-199), the default;
  *   LBM_AXIS_ORDER_ZYX  z, y, then x.  lbmCommStep then keeps the z and y faces under the
- *                       interior kernel and exchanges the x faces AFTER it, unsplit: an x shell
- *                       touches both ends of every row of the sub-domain (one DRAM page per
- *                       row and slot) and costs half a step whatever its width, the exposed x
- *                       exchange a few per cent -- use it when the decomposition cuts x.
+ *                       interior kernel and does not split an x shell off (it would touch both ends
+ *                       of every row of the sub-domain -- one DRAM page per row and slot -- and cost
+ *                       half a step whatever its width).  Instead the x faces leave the step kernels
+ *                       themselves: the threads that own the cells next to an x ghost face store the
+ *                       5 populations the neighbour consumes straight into its receive block (peer
+ *                       stores from registers, no strided gather afterwards); behind the step kernel
+ *                       a small rim pass forwards the edge lines the y/z phases delivered and raises
+ *                       the flag, then wait + unpack.  Use it when the decomposition cuts x.
+ *                       (5-slot payload only; LBM_B200_XFUSE=0 falls back to a separate x push kernel.)
  * Every rank of a run must use the same order.  LBM_B200_AXIS_ORDER=xyz|zyx presets it. */
 #define LBM_AXIS_ORDER_XYZ 0
 #define LBM_AXIS_ORDER_ZYX 1

@@ -54,8 +54,29 @@ def main():
                    compute_stream=compute_stream.cuda_stream, comm_stream=comm_stream.cuda_stream)
     mgr.initSimulation(rank)
     ctrl = mgr.getController()
-    for _ in range(steps):
+    if os.environ.get("LBM_TEST_GRAPH") == "1":
+        # what `bench.py --graph` does: capture the beta+alpha cycle once, replay it.  The halo sequence
+        # numbers are device-resident, so every replay must synchronise with the neighbour like an eager step.
+        assert steps % 2 == 0 and steps >= 4
         ctrl.computeNextStep()
+        ctrl.computeNextStep()
+        torch.cuda.synchronize()
+        dist.barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=compute_stream, capture_error_mode="thread_local"):
+            ctrl.computeNextStep()
+            ctrl.computeNextStep()
+        # the capture launched nothing; the step counter of the library advanced by two: rewind it
+        sv = ctrl.getSolver()
+        sv.simulation_step_counter = sv.simulation_step_counter - 2
+        with torch.cuda.stream(compute_stream):
+            for _ in range((steps - 2) // 2):
+                graph.replay()
+        torch.cuda.synchronize()
+        sv.simulation_step_counter = steps
+    else:
+        for _ in range(steps):
+            ctrl.computeNextStep()
     s = ctrl.getSolver()
     s.wait()
     torch.cuda.synchronize()

@@ -34,13 +34,14 @@ def _free_port():
     return p
 
 
-def _run_ranks(tmp_path, D, nums, steps, sync, axis_order="", order="linear", cs=0.0, dtype="f32", share=False):
+def _run_ranks(tmp_path, D, nums, steps, sync, axis_order="", order="linear", cs=0.0, dtype="f32", share=False,
+               graph=False):
     world = nums[0] * nums[1] * nums[2]
     if _gpus() < world and not share:
         pytest.skip("needs %d GPUs" % world)
     env = dict(os.environ, LBM_TEST_DOMAIN=",".join(map(str, D)), LBM_TEST_NUMS=",".join(map(str, nums)),
                LBM_TEST_STEPS=str(steps), LBM_TEST_SYNC=sync, LBM_TEST_OUT=str(tmp_path),
-               LBM_TEST_AXIS_ORDER=axis_order, LBM_TEST_BETA_ORDER=order, LBM_TEST_CS=repr(cs), LBM_TEST_DTYPE=dtype)
+               LBM_TEST_AXIS_ORDER=axis_order, LBM_TEST_BETA_ORDER=order, LBM_TEST_CS=repr(cs), LBM_TEST_DTYPE=dtype, LBM_TEST_GRAPH="1" if graph else "0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "_gpu_rank_worker.py")]
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
@@ -77,6 +78,16 @@ def test_two_processes_sharing_one_gpu(tmp_path, D, nums, steps, sync, axis_orde
     """The multi-process path (CUDA IPC mapped receive blocks, device-side flags) on whatever the box
     has -- two processes time-slice one GPU when there is only one.  Bench defaults otherwise."""
     _run_ranks(tmp_path, D, nums, steps, sync, axis_order, order="shipped", cs=0.1, share=True)
+
+
+@pytest.mark.parametrize("D,nums,steps,axis_order", [
+    ((40, 24, 32), (1, 1, 2), 104, ""),          # 51 replays of the captured beta+alpha cycle, z-slabs
+    ((80, 24, 16), (2, 1, 1), 104, "zyx"),       # x faces pushed from inside the step kernels
+])
+def test_cuda_graph_replay_keeps_synchronising(tmp_path, D, nums, steps, axis_order):
+    """`bench.py --graph` with the p2p transport: the captured 2-step cycle replayed 51 times must equal the
+    oracle's decomposed run -- the halo sequence numbers are counted on the device, not frozen in the graph."""
+    _run_ranks(tmp_path, D, nums, steps, "p2p", axis_order, order="shipped", cs=0.1, share=True, graph=True)
 
 
 @pytest.mark.parametrize("D,nums,steps,sync", [

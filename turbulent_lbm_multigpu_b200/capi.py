@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(HERE, "lib", "liblbm_b200.so")
 
 LBM_OK = 0
+LBM_ERR_INVALID, LBM_ERR_CUDA, LBM_ERR_NO_DEVICE, LBM_ERR_TIMEOUT = 1, 2, 3, 4
 LBM_F32, LBM_F64 = 0, 1
 LBM_BETA_ORDER_SHIPPED, LBM_BETA_ORDER_LINEAR = 0, 1
 LBM_HALO_SLOTS_REFERENCE, LBM_HALO_SLOTS_MINIMAL = 0, 1

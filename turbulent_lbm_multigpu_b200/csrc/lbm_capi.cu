@@ -37,14 +37,20 @@ struct lbm_face {
 	size_t peer_stage_off[2];                             /* layout of the block I write into */
 	char *local_block; size_t local_bytes;                /* [flags 256 B][alpha staging][beta staging] */
 	char *peer_block; bool peer_is_ipc; bool connected;
-	unsigned int *block_counter;                          /* device, for the push kernel */
+	/* device words of this face: [0..1] syncs pushed per kind, [2..3] syncs pulled per kind,
+	 * [4] block counter of the running push launch.  The sequence numbers live on the device so
+	 * that a captured CUDA graph of the step keeps counting when it is replayed. */
+	unsigned int *counters;
 };
 
 struct lbm_solver {
 	lbm_desc desc;
 	std::vector<lbm_face> faces;
-	unsigned int sync_seq[2];
 	int axis_order;              /* LBM_AXIS_ORDER_*: phase order of a sync */
+	int x_in_kernel;             /* 1 + sync kind whose x faces the last step kernels pushed themselves (XPUSH), 0 = none */
+	int xfuse;                   /* fused x push allowed (LBM_B200_XFUSE=0 turns it off) */
+	unsigned int *d_error;       /* device word: a halo wait gave up (neighbour never arrived) */
+	unsigned long long wait_timeout_ns;
 	int device;
 	int dtype;
 	int sx, sy, sz;
@@ -134,10 +140,35 @@ struct LaunchScope {
 	}
 };
 
+uint32_t popcount19(uint32_t m);
+
+/* fused x push: only with the z,y,x phase order, the 5-slot payload and every x face connected */
+bool x_fusable(lbm_t h)
+{
+	if (!h->xfuse || h->axis_order != LBM_AXIS_ORDER_ZYX) return false;
+	bool any = false;
+	for (size_t i = 0; i < h->faces.size(); i++) {
+		const lbm_face &f = h->faces[i];
+		if (f.axis != 0) continue;
+		if (!f.connected || popcount19(f.send_mask[0]) != 5 || popcount19(f.send_mask[1]) != 5) return false;
+		any = true;
+	}
+	return any;
+}
+
 template <typename T>
-StepParams<T> make_params(lbm_t h, const Box &b)
+StepParams<T> make_params(lbm_t h, const Box &b, bool alpha, bool xpush)
 {
 	StepParams<T> P;
+	P.xstage[0] = P.xstage[1] = NULL;
+	P.xface_n = (long long)h->sy * h->sz;
+	if (xpush) {
+		const int kind = alpha ? LBM_SYNC_ALPHA : LBM_SYNC_BETA;
+		for (size_t i = 0; i < h->faces.size(); i++) {
+			const lbm_face &f = h->faces[i];
+			if (f.axis == 0) P.xstage[f.dir[0] > 0 ? 0 : 1] = (T *)(f.peer_block + f.peer_stage_off[kind]);
+		}
+	}
 	P.dd = (T *)h->dd; P.flags = h->flags; P.velocity = (T *)h->velocity; P.density = (T *)h->density;
 	P.n = h->n; P.ns = h->stride; P.sx = h->sx; P.sy = h->sy; P.sz = h->sz; P.sxy = (long long)h->sx * h->sy;
 	P.inv_tau = (T)h->desc.inv_tau; P.tau = (T)h->desc.tau;
@@ -157,20 +188,22 @@ StepParams<T> make_params(lbm_t h, const Box &b)
 	return P;
 }
 
-template <typename T, int VEC, bool SMAG, bool STORE>
+template <typename T, int VEC, bool SMAG, bool STORE, bool XPUSH>
 void launch_alpha(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStream_t s, cudaStream_t)
 {
 	LaunchScope ls(h, "lbm_kernel_alpha", s);
-	lbm_alpha_kernel<T, VEC, SMAG, STORE><<<grid, block, 0, s>>>(P);
+	lbm_alpha_kernel<T, VEC, SMAG, STORE, XPUSH><<<grid, block, 0, s>>>(P);
 }
 
-template <typename T, int VEC, bool SMAG, bool STORE>
+template <typename T, int VEC, bool SMAG, bool STORE, bool XPUSH>
 void launch_beta(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStream_t s, cudaStream_t sg)
 {
 	const bool shipped = h->desc.beta_order == LBM_BETA_ORDER_SHIPPED;
 	/* general kernel: only z planes whose blocks can reach across the array ends
-	 * (|delta| <= sxy + sx + 1 -> planes 0,1 and sz-2,sz-1), or everything with the quirk */
-	const int zlo_end = P.wg > 0 ? P.sz : 2, zhi_begin = P.wg > 0 ? P.sz : P.sz - 2;
+	 * (|delta| <= sxy + sx + 1 -> planes 0,1 and sz-2,sz-1 when sy >= 2; one more when sy == 1),
+	 * or everything with the quirk */
+	const int reach_planes = (int)((P.sxy + P.sx + 1 + P.sxy - 1) / P.sxy);
+	const int zlo_end = P.wg > 0 ? P.sz : reach_planes, zhi_begin = P.wg > 0 ? P.sz : P.sz - reach_planes;
 	/* the box is one z range [a0,a1) or two ([a0,a1) below [b0,b1)): the low general planes can
 	 * only lie in the first piece, the high ones only in the last */
 	const bool two = P.zsplit < P.nz;
@@ -191,35 +224,36 @@ void launch_beta(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStr
 		dim3 g2(grid.x, (unsigned)Q.nz);
 		/* with the quirk live this launch IS the whole beta step */
 		LaunchScope ls(h, P.wg > 0 ? "lbm_kernel_beta" : "lbm_kernel_beta.wrap", sg);
-		if (shipped) lbm_beta_general_kernel<T, VEC, SMAG, STORE, 0><<<g2, block, 0, sg>>>(Q);
-		else lbm_beta_general_kernel<T, VEC, SMAG, STORE, 1><<<g2, block, 0, sg>>>(Q);
+		if (shipped) lbm_beta_general_kernel<T, VEC, SMAG, STORE, 0, XPUSH><<<g2, block, 0, sg>>>(Q);
+		else lbm_beta_general_kernel<T, VEC, SMAG, STORE, 1, XPUSH><<<g2, block, 0, sg>>>(Q);
 	}
 	/* the vectorised kernel second: when sg is another stream the small wrapping kernel is
 	 * already resident and both run side by side */
 	if (P.wg == 0) {   /* with the work-group quirk live every block takes the general path */
 		LaunchScope ls(h, "lbm_kernel_beta", s);
-		if (shipped) lbm_beta_kernel<T, VEC, SMAG, STORE, 0><<<grid, block, 0, s>>>(P);
-		else lbm_beta_kernel<T, VEC, SMAG, STORE, 1><<<grid, block, 0, s>>>(P);
+		if (shipped) lbm_beta_kernel<T, VEC, SMAG, STORE, 0, XPUSH><<<grid, block, 0, s>>>(P);
+		else lbm_beta_kernel<T, VEC, SMAG, STORE, 1, XPUSH><<<grid, block, 0, s>>>(P);
 	}
 }
 
 template <typename T, int VEC>
-int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream_t sg)
+int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream_t sg, bool xpush)
 {
 	if (b.nx <= 0 || b.ny <= 0 || b.nz + b.nzb <= 0) return LBM_OK;
-	const StepParams<T> P = make_params<T>(h, b);
+	const StepParams<T> P = make_params<T>(h, b, alpha, xpush);
 	const long long groups = ((long long)b.nx * b.ny) / VEC;
 	dim3 block(h->block);
 	dim3 grid((unsigned)((groups + h->block - 1) / h->block), (unsigned)(b.nz + b.nzb));
 	const bool store = h->desc.store_velocity || h->desc.store_density;
-#define LBM_DISPATCH(FN)                                              \
+#define LBM_DISPATCH(FN, XP)                                          \
 	do {                                                              \
-		if (h->smag) { if (store) FN<T, VEC, true, true>(h, P, grid, block, s, sg);   \
-		               else       FN<T, VEC, true, false>(h, P, grid, block, s, sg); }\
-		else         { if (store) FN<T, VEC, false, true>(h, P, grid, block, s, sg);  \
-		               else       FN<T, VEC, false, false>(h, P, grid, block, s, sg); } \
+		if (h->smag) { if (store) FN<T, VEC, true, true, XP>(h, P, grid, block, s, sg);   \
+		               else       FN<T, VEC, true, false, XP>(h, P, grid, block, s, sg); }\
+		else         { if (store) FN<T, VEC, false, true, XP>(h, P, grid, block, s, sg);  \
+		               else       FN<T, VEC, false, false, XP>(h, P, grid, block, s, sg); } \
 	} while (0)
-	if (alpha) LBM_DISPATCH(launch_alpha); else LBM_DISPATCH(launch_beta);
+	if (xpush) { if (alpha) LBM_DISPATCH(launch_alpha, true); else LBM_DISPATCH(launch_beta, true); }
+	else       { if (alpha) LBM_DISPATCH(launch_alpha, false); else LBM_DISPATCH(launch_beta, false); }
 #undef LBM_DISPATCH
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
@@ -227,19 +261,19 @@ int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream
 
 /* s: stream of the step kernel; sg: stream of beta's wrapping ("general") kernel -- the two
  * touch disjoint (slot, location) pairs, so sg may be a stream that runs concurrently with s */
-int launch_step(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream_t sg = NULL)
+int launch_step(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream_t sg = NULL, bool xpush = false)
 {
 	if (!sg) sg = s;
 	if (h->dtype == LBM_F32) {
 		switch (h->vec) {
-		case 4: return launch_step_tv<float, 4>(h, alpha, b, s, sg);
-		case 2: return launch_step_tv<float, 2>(h, alpha, b, s, sg);
-		default: return launch_step_tv<float, 1>(h, alpha, b, s, sg);
+		case 4: return launch_step_tv<float, 4>(h, alpha, b, s, sg, xpush);
+		case 2: return launch_step_tv<float, 2>(h, alpha, b, s, sg, xpush);
+		default: return launch_step_tv<float, 1>(h, alpha, b, s, sg, xpush);
 		}
 	}
 	switch (h->vec) {
-	case 2: return launch_step_tv<double, 2>(h, alpha, b, s, sg);
-	default: return launch_step_tv<double, 1>(h, alpha, b, s, sg);
+	case 2: return launch_step_tv<double, 2>(h, alpha, b, s, sg, xpush);
+	default: return launch_step_tv<double, 1>(h, alpha, b, s, sg, xpush);
 	}
 }
 
@@ -257,7 +291,7 @@ void partition(lbm_t h, int ghost_faces, std::vector<Box> &shell, Box &interior)
 	int lo[3], hi[3];
 	for (int a = 0; a < 3; a++) {
 		int t = 2;
-		if (a == 0) { t = h->xshell; while (t > 2 && (t > S[0] / 4 || (S[0] % t) != 0)) t >>= 1; if (t < h->vec) t = h->vec; if (t < 2) t = 2; }
+		if (a == 0) { t = h->xshell; while (t > 2 && (t > S[0] / 4 || (S[0] % t) != 0)) t >>= 1; if (t < 2) t = 2; t = (t + h->vec - 1) / h->vec * h->vec; }   /* whole vectors: box x0/nx stay multiples of VEC */
 		lo[a] = (ghost_faces >> (2 * a)) & 1 ? t : 0;
 		hi[a] = (ghost_faces >> (2 * a + 1)) & 1 ? S[a] - t : S[a];
 		if (lo[a] > hi[a]) { lo[a] = 0; hi[a] = 0; }   /* everything is shell */
@@ -359,8 +393,12 @@ int store_field(lbm_t h, const void *field, size_t elem, int comps, void *host_d
 	if (int rc = use_device(h)) return rc;
 	if (!host_dst) return fail(h, LBM_ERR_INVALID, "null host pointer");
 	if (!origin || !size) {
-		CUDA_TRY(h, cudaMemcpy2DAsync(host_dst, (size_t)h->n * elem, field, (size_t)field_stride * elem,
-				(size_t)h->n * elem, comps, cudaMemcpyDeviceToHost, h->compute));
+		/* no cudaMemcpy2D: its pitch is capped at 2 GiB, a sub-domain slot is not */
+		if (field_stride == h->n)
+			CUDA_TRY(h, cudaMemcpyAsync(host_dst, field, (size_t)comps * h->n * elem, cudaMemcpyDeviceToHost, h->compute));
+		else for (int c = 0; c < comps; c++)
+			CUDA_TRY(h, cudaMemcpyAsync((char *)host_dst + (size_t)c * h->n * elem, (const char *)field + (size_t)c * field_stride * elem,
+					(size_t)h->n * elem, cudaMemcpyDeviceToHost, h->compute));
 		CUDA_TRY(h, cudaStreamSynchronize(h->compute));
 		return LBM_OK;
 	}
@@ -385,8 +423,11 @@ int set_field(lbm_t h, void *field, size_t elem, int comps, const void *host_src
 	if (int rc = use_device(h)) return rc;
 	if (!host_src) return fail(h, LBM_ERR_INVALID, "null host pointer");
 	if (!origin || !size) {
-		CUDA_TRY(h, cudaMemcpy2DAsync(field, (size_t)field_stride * elem, host_src, (size_t)h->n * elem,
-				(size_t)h->n * elem, comps, cudaMemcpyHostToDevice, h->compute));
+		if (field_stride == h->n)
+			CUDA_TRY(h, cudaMemcpyAsync(field, host_src, (size_t)comps * h->n * elem, cudaMemcpyHostToDevice, h->compute));
+		else for (int c = 0; c < comps; c++)
+			CUDA_TRY(h, cudaMemcpyAsync((char *)field + (size_t)c * field_stride * elem, (const char *)host_src + (size_t)c * h->n * elem,
+					(size_t)h->n * elem, cudaMemcpyHostToDevice, h->compute));
 		CUDA_TRY(h, cudaStreamSynchronize(h->compute));
 		return LBM_OK;
 	}
@@ -415,7 +456,7 @@ const int kUnits[19][3] = {
 	{ 0, 1, 1 }, { 0, -1, -1 }, { 0, 1, -1 }, { 0, -1, 1 },
 	{ 0, 0, 1 }, { 0, 0, -1 }, { 0, 0, 0 } };
 
-int popcount19(uint32_t m) { int c = 0; for (int f = 0; f < 19; f++) c += (m >> f) & 1; return c; }
+uint32_t popcount19(uint32_t m) { uint32_t c = 0; for (int f = 0; f < 19; f++) c += (m >> f) & 1; return c; }
 
 } // namespace
 
@@ -471,7 +512,11 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	h->profile_mode = 0; h->prof_base = NULL; h->prof_dropped = 0;
 	h->xshell = 32;
 	if (const char *e = getenv("LBM_B200_XSHELL")) h->xshell = atoi(e) > 1 ? atoi(e) : 2;
-	h->sync_seq[0] = h->sync_seq[1] = 0;
+	h->x_in_kernel = 0; h->d_error = NULL;
+	h->xfuse = 1;
+	if (const char *e = getenv("LBM_B200_XFUSE")) h->xfuse = atoi(e) != 0;
+	h->wait_timeout_ns = 30ull * 1000000000ull;
+	if (const char *e = getenv("LBM_B200_WAIT_TIMEOUT_MS")) if (atoll(e) > 0) h->wait_timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
 	h->axis_order = LBM_AXIS_ORDER_XYZ;
 	if (const char *e = getenv("LBM_B200_AXIS_ORDER")) if (!strcmp(e, "zyx") || !strcmp(e, "ZYX")) h->axis_order = LBM_AXIS_ORDER_ZYX;
 	h->smag = d->smagorinsky_cs != 0.0;
@@ -512,6 +557,8 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	CREATE_TRY(cudaMemsetAsync(h->dd, 0, (size_t)19 * h->stride * h->elem, h->compute));
 	CREATE_TRY(cudaMalloc((void **)&h->flags, (size_t)h->n * sizeof(int)));
 	CREATE_TRY(cudaMalloc((void **)&h->d_checksum, sizeof(double)));
+	CREATE_TRY(cudaMalloc((void **)&h->d_error, sizeof(unsigned int)));
+	CREATE_TRY(cudaMemsetAsync(h->d_error, 0, sizeof(unsigned int), h->compute));
 	if (d->store_velocity) { CREATE_TRY(cudaMalloc(&h->velocity, (size_t)3 * h->n * h->elem)); }
 	if (d->store_density) { CREATE_TRY(cudaMalloc(&h->density, (size_t)h->n * h->elem)); }
 #undef CREATE_TRY
@@ -533,8 +580,9 @@ int lbmDestroy(lbm_t h)
 	for (size_t i = 0; i < h->faces.size(); i++) {
 		lbm_face &f = h->faces[i];
 		if (f.peer_is_ipc && f.peer_block) cudaIpcCloseMemHandle(f.peer_block);
-		cudaFree(f.local_block); cudaFree(f.block_counter);
+		cudaFree(f.local_block); cudaFree(f.counters);
 	}
+	cudaFree(h->d_error);
 	cudaFree(h->dd); cudaFree(h->flags); cudaFree(h->velocity); cudaFree(h->density);
 	cudaFree(h->staging); cudaFree(h->d_checksum);
 	if (h->ev_compute) cudaEventDestroy(h->ev_compute);
@@ -599,6 +647,7 @@ int lbmStep(lbm_t h)
 	CHECK_HANDLE(h);
 	/* CLbmSolver::simulationStep, src/CLbmSolver.hpp:664-676 */
 	int rc = (h->counter & 1) ? lbmStepAlpha(h) : lbmStepBeta(h);
+	h->x_in_kernel = 0;
 	if (rc == LBM_OK) h->counter++;
 	return rc;
 }
@@ -617,8 +666,10 @@ static int step_shell_on(lbm_t h, int ghost_faces, cudaStream_t s)
 	std::vector<Box> shell; Box interior;
 	partition(h, ghost_faces, shell, interior);
 	const bool alpha = (h->counter & 1) != 0;
+	/* x faces that are not split off (z,y,x order) leave the step kernels themselves */
+	const bool xpush = (ghost_faces & 3) == 0 && x_fusable(h);
 	for (size_t i = 0; i < shell.size(); i++)
-		if (int rc = launch_step(h, alpha, shell[i], s)) return rc;
+		if (int rc = launch_step(h, alpha, shell[i], s, NULL, xpush)) return rc;
 	return LBM_OK;
 }
 
@@ -641,7 +692,9 @@ int lbmStepInterior(lbm_t h, int ghost_faces)
 	std::vector<Box> shell; Box interior;
 	partition(h, ghost_faces, shell, interior);
 	const bool alpha = (h->counter & 1) != 0;
-	if (int rc = launch_step(h, alpha, interior, h->compute, h->step_aux)) return rc;
+	const bool xpush = (ghost_faces & 3) == 0 && x_fusable(h);
+	if (int rc = launch_step(h, alpha, interior, h->compute, h->step_aux, xpush)) return rc;
+	h->x_in_kernel = xpush ? 1 + (alpha ? LBM_SYNC_ALPHA : LBM_SYNC_BETA) : 0;
 	h->counter++;
 	return LBM_OK;
 }
@@ -674,6 +727,14 @@ int lbmWait(lbm_t h)
 	if (int rc = use_device(h)) return rc;
 	CUDA_TRY(h, cudaStreamSynchronize(h->compute));
 	CUDA_TRY(h, cudaStreamSynchronize(h->comm));
+	if (!h->faces.empty()) {
+		unsigned int err = 0;
+		CUDA_TRY(h, cudaMemcpy(&err, h->d_error, sizeof(err), cudaMemcpyDeviceToHost));
+		if (err) {
+			CUDA_TRY(h, cudaMemset(h->d_error, 0, sizeof(err)));
+			return fail(h, LBM_ERR_TIMEOUT, "halo wait timed out: a neighbour never pushed its face (LBM_B200_WAIT_TIMEOUT_MS)");
+		}
+	}
 	return LBM_OK;
 }
 
@@ -915,16 +976,20 @@ void fill_face(lbm_t h, HaloFace &F, const int origin[3], const int size[3])
 	F.vec = face_vec(h, origin, size);
 }
 
-unsigned face_blocks(const HaloFace &F)
+/* hidden = the kernel shares the SMs with the step kernel (few blocks: every push block ends with a
+ * system fence); exposed = it runs alone behind the step kernel (x faces): use the whole machine */
+unsigned face_blocks(const HaloFace &F, bool exposed)
 {
 	const long long work = ((long long)F.size[0] * F.size[1] * F.size[2] * F.ncomp) / F.vec;
 	long long g = (work + 255) / 256;
-	if (g > 148) g = 148;               /* few blocks: every block ends with a system fence (push) or spins (pull) */
+	const long long cap = exposed ? 148 * 8 : 148;
+	if (g > cap) g = cap;
 	return (unsigned)(g < 1 ? 1 : g);
 }
 
-/* every face of one axis in ONE launch on the comm stream */
-int axis_push(lbm_t h, int kind, int axis, cudaStream_t s)
+/* every face of one axis in ONE launch.  rim_only: the bulk of the (x) faces already left the step
+ * kernels (XPUSH); send the rim lines and raise the flags. */
+int axis_push(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed, bool rim_only)
 {
 	HaloAxis A;
 	memset(&A, 0, sizeof(A));
@@ -941,23 +1006,35 @@ int axis_push(lbm_t h, int kind, int axis, cudaStream_t s)
 		F.ncomp = n;
 		F.staging = f.peer_block + f.peer_stage_off[kind];
 		F.flag = (volatile unsigned int *)(f.peer_block + 64 * kind);
-		F.block_counter = f.block_counter;
-		const unsigned b = face_blocks(F);
+		F.sync_count = f.counters + kind;
+		F.block_counter = f.counters + 4;
+		unsigned b = face_blocks(F, exposed);
+		if (rim_only) {
+			const long long work = 4LL * (F.size[1] + F.size[2]) * F.ncomp;
+			b = (unsigned)((work + 255) / 256);
+			if (b > 148) b = 148;
+			if (b < 1) b = 1;
+		}
 		if (b > blocks) blocks = b;
 		nf++;
 	}
 	if (nf == 0) return LBM_OK;
 	dim3 grid(blocks, nf);
-	{
-	LaunchScope ls(h, "halo_push", s);
-	if (h->dtype == LBM_F32) halo_push_kernel<float><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
-	else halo_push_kernel<double><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
+	if (rim_only) {
+		LaunchScope ls(h, "halo_xrim", s);
+		if (h->dtype == LBM_F32) halo_xrim_flag_kernel<float><<<grid, 256, 0, s>>>(A);
+		else halo_xrim_flag_kernel<double><<<grid, 256, 0, s>>>(A);
+	} else {
+		LaunchScope ls(h, "halo_push", s);
+		if (h->dtype == LBM_F32) halo_push_kernel<float><<<grid, 256, 0, s>>>(A);
+		else halo_push_kernel<double><<<grid, 256, 0, s>>>(A);
 	}
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
 }
 
-int axis_pull(lbm_t h, int kind, int axis, cudaStream_t s)
+/* wait (one thread per face) + unpack, two launches in stream order */
+int axis_pull(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed)
 {
 	HaloAxis A;
 	memset(&A, 0, sizeof(A));
@@ -977,17 +1054,23 @@ int axis_pull(lbm_t h, int kind, int axis, cudaStream_t s)
 		F.ncomp = n;
 		F.staging = f.local_block + f.stage_off[kind];
 		F.flag = (volatile unsigned int *)(f.local_block + 64 * kind);
+		F.sync_count = f.counters + 2 + kind;
 		F.block_counter = NULL;
-		const unsigned b = face_blocks(F);
+		const unsigned b = face_blocks(F, exposed);
 		if (b > blocks) blocks = b;
 		nf++;
 	}
 	if (nf == 0) return LBM_OK;
+	{
+	LaunchScope ls(h, "halo_wait", s);
+	halo_wait_kernel<<<1, 32, 0, s>>>(A, (int)nf, h->wait_timeout_ns, h->d_error);
+	}
+	CUDA_TRY(h, cudaGetLastError());
 	dim3 grid(blocks, nf);
 	{
 	LaunchScope ls(h, "halo_pull", s);
-	if (h->dtype == LBM_F32) halo_pull_kernel<float><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
-	else halo_pull_kernel<double><<<grid, 256, 0, s>>>(A, h->sync_seq[kind]);
+	if (h->dtype == LBM_F32) halo_unpack_kernel<float><<<grid, 256, 0, s>>>(A);
+	else halo_unpack_kernel<double><<<grid, 256, 0, s>>>(A);
 	}
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
@@ -1038,8 +1121,8 @@ int lbmCommAddFace(lbm_t h, int dst_rank, const int send_origin[3], const int re
 	f.local_bytes = off;
 	CUDA_TRY(h, cudaMalloc((void **)&f.local_block, f.local_bytes));
 	CUDA_TRY(h, cudaMemset(f.local_block, 0, 256));
-	CUDA_TRY(h, cudaMalloc((void **)&f.block_counter, sizeof(unsigned int)));
-	CUDA_TRY(h, cudaMemset(f.block_counter, 0, sizeof(unsigned int)));
+	CUDA_TRY(h, cudaMalloc((void **)&f.counters, 8 * sizeof(unsigned int)));
+	CUDA_TRY(h, cudaMemset(f.counters, 0, 8 * sizeof(unsigned int)));
 	h->faces.push_back(f);
 	if (face_id) *face_id = (int)h->faces.size() - 1;
 	return LBM_OK;
@@ -1109,22 +1192,26 @@ int lbmCommBeginSync(lbm_t h, int sync_kind)
 {
 	CHECK_HANDLE(h);
 	if (sync_kind != LBM_SYNC_ALPHA && sync_kind != LBM_SYNC_BETA) return fail(h, LBM_ERR_INVALID, "bad sync kind");
-	h->sync_seq[sync_kind]++;
+	/* nothing to do: the sequence numbers are counted by the push / wait kernels in device memory */
 	return LBM_OK;
 }
 
 int lbmCommPush(lbm_t h, int sync_kind, int axis)
 {
 	CHECK_HANDLE(h);
+	if (sync_kind != LBM_SYNC_ALPHA && sync_kind != LBM_SYNC_BETA) return fail(h, LBM_ERR_INVALID, "bad sync kind");
 	if (int rc = use_device(h)) return rc;
-	return axis_push(h, sync_kind, axis, h->comm);
+	const bool rim_only = axis == 0 && h->x_in_kernel == 1 + sync_kind;
+	if (axis == 0) h->x_in_kernel = 0;
+	return axis_push(h, sync_kind, axis, h->comm, false, rim_only);
 }
 
 int lbmCommPull(lbm_t h, int sync_kind, int axis)
 {
 	CHECK_HANDLE(h);
+	if (sync_kind != LBM_SYNC_ALPHA && sync_kind != LBM_SYNC_BETA) return fail(h, LBM_ERR_INVALID, "bad sync kind");
 	if (int rc = use_device(h)) return rc;
-	return axis_pull(h, sync_kind, axis, h->comm);
+	return axis_pull(h, sync_kind, axis, h->comm, false);
 }
 
 int lbmCommSetAxisOrder(lbm_t h, int order)
@@ -1161,7 +1248,7 @@ static int comm_step(lbm_t h, cudaEvent_t *marks /* NULL or 5 timing events */)
 {
 	if (int rc = use_device(h)) return rc;
 	const int faces = ghost_mask_of_faces(h);
-	/* z,y,x order: x faces are not split off; they are exchanged after the interior kernel */
+	/* z,y,x order: x faces are not split off; they are exchanged after the step kernel */
 	const bool x_last = h->axis_order == LBM_AXIS_ORDER_ZYX && (faces & 3) != 0;
 	const int split = x_last ? (faces & ~3) : faces;
 	const int kind = (h->counter & 1) ? LBM_SYNC_ALPHA : LBM_SYNC_BETA;   /* the sync that follows this step */
@@ -1180,19 +1267,24 @@ static int comm_step(lbm_t h, cudaEvent_t *marks /* NULL or 5 timing events */)
 	if (marks) CUDA_TRY(h, cudaEventRecord(marks[2], h->compute));
 	if (!x_last) {
 		if (int rc = lbmCommSync(h, kind)) return rc;
+		if (marks) CUDA_TRY(h, cudaEventRecord(marks[3], h->comm));
+		if (int rc = lbmStreamWaitStream(h, 0)) return rc;     /* join: the next step needs the halo */
 	} else {
-		if (int rc = lbmCommBeginSync(h, kind)) return rc;
-		for (int axis = 2; axis >= 1; axis--) {             /* hidden under the interior kernel */
-			if (int rc = lbmCommPush(h, kind, axis)) return rc;
-			if (int rc = lbmCommPull(h, kind, axis)) return rc;
+		for (int axis = 2; axis >= 1; axis--) {                 /* hidden under the interior kernel */
+			if (int rc = axis_push(h, kind, axis, h->comm, false, false)) return rc;
+			if (int rc = axis_pull(h, kind, axis, h->comm, false)) return rc;
 		}
-		/* the x faces hold cells the interior kernel updates: the comm stream picks up behind it */
-		if (int rc = lbmStreamWaitStream(h, 1)) return rc;
-		if (int rc = lbmCommPush(h, kind, 0)) return rc;
-		if (int rc = lbmCommPull(h, kind, 0)) return rc;
+		/* join first: the x faces follow the step kernel AND the y/z unpack (whose rims they forward),
+		 * on the compute stream itself -- no further stream hop between them and the next step.
+		 * Their bulk is already in the neighbour's block (XPUSH step kernels): rim lines + flag, then
+		 * wait + unpack with the whole machine. */
+		if (int rc = lbmStreamWaitStream(h, 0)) return rc;
+		const bool rim_only = h->x_in_kernel == 1 + kind;
+		h->x_in_kernel = 0;
+		if (int rc = axis_push(h, kind, 0, h->compute, true, rim_only)) return rc;
+		if (int rc = axis_pull(h, kind, 0, h->compute, true)) return rc;
+		if (marks) CUDA_TRY(h, cudaEventRecord(marks[3], h->compute));
 	}
-	if (marks) CUDA_TRY(h, cudaEventRecord(marks[3], h->comm));
-	if (int rc = lbmStreamWaitStream(h, 0)) return rc;     /* join: the next step needs the halo */
 	if (marks) CUDA_TRY(h, cudaEventRecord(marks[4], h->compute));
 	return LBM_OK;
 }

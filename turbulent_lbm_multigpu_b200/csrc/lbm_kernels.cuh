@@ -58,7 +58,22 @@ struct StepParams {
 	 * offset read from the constant bank: cheap to rematerialise for the push, which keeps 18
 	 * 64-bit pointers out of the register file between pull and push (see beta_uses_offset_table) */
 	long long boff[18];
+	/* fused x-face halo push (XPUSH instantiations; lbmCommStep with the z,y,x phase order): the
+	 * thread that owns the cell next to an x ghost face (x = 1 / x = sx-2) holds the 5 populations
+	 * the x neighbour consumes in registers and stores them straight into the neighbour's receive
+	 * block [position][z][y] (peer memory over NVLink) -- no strided gather kernel afterwards.
+	 * xstage[side] == NULL: that side has no neighbour. */
+	T *xstage[2];
+	long long xface_n;       /* sy * sz: cells of an x face = stride between staging positions */
 };
+
+/* slots an x face ships, ascending = their position in the staging block.
+ *   toward +x (e_x = +1): what the LOW face sends after an alpha step (my x=1 column -> the neighbour's
+ *                         high ghost column) and what the HIGH face sends after a beta step (my high ghost
+ *                         column -> the neighbour's x=1 column);
+ *   toward -x (e_x = -1): the other two cases.  (lbmHaloSlotMask, 5-slot payload) */
+__device__ __constant__ const int kXPlus[5] = { 0, 4, 6, 8, 10 };
+__device__ __constant__ const int kXMinus[5] = { 1, 5, 7, 9, 11 };
 
 /* ---------------------------------------------------------------- vector access
  * Cache-operator tuning knobs for the ALIGNED slot streams (each value is touched once per step,
@@ -447,23 +462,41 @@ __device__ __forceinline__ int box_z(const StepParams<T> &P)
 
 /* thread -> first cell of its VEC-wide group inside the iteration box; false = out of box */
 template <typename T, int VEC>
-__device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
+__device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid, long long &off)
 {
 	const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
 	if (t >= (long long)P.nx * P.ny) return false;
-	long long off;
 	if (P.nx == P.sx) off = (long long)P.y0 * P.sx + t;
 	else { const int iy = (int)(t / P.nx), ix = (int)(t - (long long)iy * P.nx); off = (long long)(P.y0 + iy) * P.sx + P.x0 + ix; }
 	gid = (long long)box_z(P) * P.sxy + off;
 	return true;
 }
+template <typename T, int VEC>
+__device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
+{
+	long long off;
+	return box_cell<T, VEC>(P, gid, off);
+}
+
+/* XPUSH: which element of this thread's VEC-wide group is the cell next to the low / high x ghost
+ * face (-1: none), and the cell's index in the face [z][y].  off = offset of the group inside its plane. */
+template <typename T, int VEC>
+__device__ __forceinline__ void xpush_lanes(const StepParams<T> &P, long long off, int &e_lo, int &e_hi, long long &rowidx)
+{
+	const unsigned int po = (unsigned int)off;                 /* a plane has < 2^32 cells */
+	const unsigned int y = po / (unsigned int)P.sx;
+	const int x0 = (int)(po - y * (unsigned int)P.sx);
+	rowidx = (long long)box_z(P) * P.sy + y;
+	e_lo = (P.xstage[0] != nullptr && x0 <= 1 && 1 < x0 + VEC) ? 1 - x0 : -1;
+	e_hi = (P.xstage[1] != nullptr && x0 <= P.sx - 2 && P.sx - 2 < x0 + VEC) ? P.sx - 2 - x0 : -1;
+}
 
 /* ================================================================== ALPHA kernel */
-template <typename T, int VEC, bool SMAG, bool STORE>
+template <typename T, int VEC, bool SMAG, bool STORE, bool XPUSH>
 __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 {
-	long long gid;
-	if (!box_cell<T, VEC>(P, gid)) return;
+	long long gid, poff;
+	if (!box_cell<T, VEC>(P, gid, poff)) return;
 
 	int flag[VEC];
 	FlagIO<VEC>::load(P.flags + gid, flag);
@@ -474,7 +507,13 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 #pragma unroll
 	for (int e = 0; e < VEC; e++) all_ghost &= (flag[e] == FLAG_GHOST);
 	if (all_ghost) return;                       /* lbm_alpha.cl:31-32 */
-	if (!any_write && !STORE) return;            /* obstacle cells write nothing (:305-343) */
+	if (!any_write && !STORE) {                  /* obstacle cells write nothing (:305-343) ... */
+		if (!XPUSH) return;
+		int e_lo, e_hi;                          /* ... but a cell next to an x face still ships its slots */
+		long long rowidx;
+		xpush_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
+		if (e_lo < 0 && e_hi < 0) return;
+	}
 
 	T v[19][VEC];
 	T *base = P.dd + gid;
@@ -501,6 +540,27 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 #pragma unroll
 		for (int i = 0; i < 18; i++) VecIO<T, VEC>::store(base + (long long)i * P.ns, v[i ^ 1]);
 		VecIO<T, VEC>::store(base + 18LL * P.ns, v[18]);
+	}
+	if (XPUSH) {
+		/* slot j holds v[j^1] after this step.  Ghost cells (rims of the y/z faces) are left to the
+		 * rim pass that follows the y/z unpack (halo_xrim_flag_kernel).  (The lane test is evaluated
+		 * here, behind the stores, so that it occupies no registers across the collision.) */
+		int e_lo, e_hi;
+		long long rowidx;
+		xpush_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
+#pragma unroll
+		for (int e = 0; e < VEC; e++) {
+			if (e == e_lo && flag[e] != FLAG_GHOST) {
+				T *st = P.xstage[0] + rowidx;
+#pragma unroll
+				for (int k = 0; k < 5; k++) st[k * P.xface_n] = v[2 * k + (k ? 3 : 1)][e];   /* slots 0,4,6,8,10 <- v[1,5,7,9,11] */
+			}
+			if (e == e_hi && flag[e] != FLAG_GHOST) {
+				T *st = P.xstage[1] + rowidx;
+#pragma unroll
+				for (int k = 0; k < 5; k++) st[k * P.xface_n] = v[2 * k + (k ? 2 : 0)][e];   /* slots 1,5,7,9,11 <- v[0,4,6,8,10] */
+			}
+		}
 	}
 	if (STORE) {
 #pragma unroll
@@ -555,11 +615,11 @@ __device__ __forceinline__ constexpr bool beta_uses_offset_table()
 	return LBM_BETA_OFFTAB == 1 || (LBM_BETA_OFFTAB == 2 && SMAG && !STORE && sizeof(T) == 4);
 }
 
-template <typename T, int VEC, bool SMAG, bool STORE, int ORDER>
+template <typename T, int VEC, bool SMAG, bool STORE, int ORDER, bool XPUSH>
 __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 {
-	long long gid;
-	if (!box_cell<T, VEC>(P, gid)) return;
+	long long gid, poff;
+	if (!box_cell<T, VEC>(P, gid, poff)) return;
 	if (beta_block_is_general<T, VEC>(P)) return;
 
 	const long long DY = P.sx, DZ = P.sxy;
@@ -613,6 +673,34 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	}
 	VecIO<T, VEC>::store(base + 18LL * P.ns, v[18]);
 
+	if (XPUSH) {
+		/* the x = 1 (x = sx-2) cell is the only writer of the e_x = -1 (+1) slots of the ghost column
+		 * next to it: location (slot j, c + e_j) has face index row(c) + e_y + e_z * sy.  Blocks on
+		 * this path are more than a plane + a row away from the array ends, so the index is in range. */
+		int e_lo, e_hi;
+		long long rowidx;
+		xpush_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
+#pragma unroll
+		for (int e = 0; e < VEC; e++) {
+			if (e == e_lo) {
+				T *st = P.xstage[0] + rowidx;
+				st[0] = v[1][e];                               /* (-1, 0, 0) */
+				st[1 * P.xface_n - 1] = v[5][e];               /* (-1,-1, 0) */
+				st[2 * P.xface_n + 1] = v[7][e];               /* (-1, 1, 0) */
+				st[3 * P.xface_n - P.sy] = v[9][e];            /* (-1, 0,-1) */
+				st[4 * P.xface_n + P.sy] = v[11][e];           /* (-1, 0, 1) */
+			}
+			if (e == e_hi) {
+				T *st = P.xstage[1] + rowidx;
+				st[0] = v[0][e];                               /* ( 1, 0, 0) */
+				st[1 * P.xface_n + 1] = v[4][e];               /* ( 1, 1, 0) */
+				st[2 * P.xface_n - 1] = v[6][e];               /* ( 1,-1, 0) */
+				st[3 * P.xface_n + P.sy] = v[8][e];            /* ( 1, 0, 1) */
+				st[4 * P.xface_n - P.sy] = v[10][e];           /* ( 1, 0,-1) */
+			}
+		}
+	}
+
 	if (STORE) {
 #pragma unroll
 		for (int e = 0; e < VEC; e++) {
@@ -627,13 +715,14 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	}
 }
 
-template <typename T, int VEC, bool SMAG, bool STORE, int ORDER>
+template <typename T, int VEC, bool SMAG, bool STORE, int ORDER, bool XPUSH>
 __global__ void lbm_beta_general_kernel(const StepParams<T> P)
 {
-	long long gid;
-	if (!box_cell<T, VEC>(P, gid)) return;
+	long long gid, poff;
+	if (!box_cell<T, VEC>(P, gid, poff)) return;
 	if (!beta_block_is_general<T, VEC>(P)) return;
 	const long long DY = P.sx, DZ = P.sxy;
+	const int gx0 = XPUSH ? (int)((unsigned int)poff % (unsigned int)P.sx) : 0;
 #pragma unroll 1
 	for (int e = 0; e < VEC; e++) {
 		const long long c = gid + e;
@@ -669,6 +758,25 @@ __global__ void lbm_beta_general_kernel(const StepParams<T> P)
 #pragma unroll
 		for (int i = 0; i < 18; i++) P.dd[L[i]] = d[i];
 		P.dd[18LL * P.ns + c] = d[18];
+		if (XPUSH) {
+			/* by LOCATION (the wrap and the work-group quirk move cells around): whatever this cell
+			 * writes into an x ghost column with a neighbour behind it also goes to that neighbour */
+			const int x = gx0 + e;
+			if (P.wg > 0 || x <= 1 || x >= P.sx - 2) {
+#pragma unroll
+				for (int k = 0; k < 5; k++) {
+					const int jm = 2 * k + (k ? 3 : 1), jp = 2 * k + (k ? 2 : 0);      /* kXMinus[k], kXPlus[k] */
+					if (P.xstage[0]) {
+						const long long loc = L[jm] - (long long)jm * P.ns;
+						if (loc % P.sx == 0) P.xstage[0][k * P.xface_n + loc / P.sx] = d[jm];
+					}
+					if (P.xstage[1]) {
+						const long long loc = L[jp] - (long long)jp * P.ns;
+						if (loc % P.sx == P.sx - 1) P.xstage[1][k * P.xface_n + loc / P.sx] = d[jp];
+					}
+				}
+			}
+		}
 		if (STORE && flag != FLAG_GHOST) {
 			if (P.store_v) { P.velocity[c] = vx; P.velocity[P.n + c] = vy; P.velocity[2 * P.n + c] = vz; }
 			if (P.store_r) P.density[c] = rho;
@@ -745,12 +853,16 @@ __global__ void rect_copy_kernel(const T *__restrict__ src, T *__restrict__ dst,
 
 /* ================================================================== peer-memory halo
  * One-sided halo exchange over NVLink peer memory (same process or CUDA-IPC mapped):
- *   halo_push_kernel  packs the selected slots of the (up to two) faces of one axis and stores
- *                     them STRAIGHT INTO the neighbours' staging buffers (peer stores: pack +
- *                     send fused); the last block of a face publishes a sequence number in the
- *                     neighbour's flag word;
- *   halo_pull_kernel  waits (acquire, system scope) until the local flags reach the expected
- *                     sequence number and unpacks the local staging buffers into the dd rects.
+ *   halo_push_kernel       packs the selected slots of the (up to two) faces of one axis and stores
+ *                          them STRAIGHT INTO the neighbours' staging buffers (peer stores: pack +
+ *                          send fused); the last block of a face publishes a sequence number in the
+ *                          neighbour's flag word;
+ *   XPUSH step kernels     the same for x faces from inside lbm_alpha/beta_kernel (the owning threads
+ *                          hold the values in registers), completed by halo_xrim_flag_kernel;
+ *   halo_wait_kernel       one thread per face waits (acquire, system scope) until the local flag
+ *                          reaches the next sequence number;
+ *   halo_unpack_kernel     unpacks the local staging buffers into the dd rects.
+ * All sequence numbers are counted in device memory: a captured CUDA graph can be replayed.
  * Replaces storeDensityDistribution -> MPI_Isend/Irecv/Waitall -> setDensityDistribution
  * (reference src/CController.hpp:265-383). */
 /* One halo face of a fused launch.  dd side: [slot][z][y][x] rect inside the sub-domain with
@@ -758,9 +870,11 @@ __global__ void rect_copy_kernel(const T *__restrict__ src, T *__restrict__ dst,
  * per thread and step (4/2 when rows are whole, aligned multiples -- y and z faces; 1 for x faces). */
 struct HaloFace {
 	void *dd;                       /* sub-domain populations (local) */
-	void *staging;                  /* push: the NEIGHBOUR's receive block (peer memory); pull: mine */
-	unsigned int *block_counter;    /* push only */
-	volatile unsigned int *flag;    /* push: the neighbour's flag word; pull: mine */
+	void *staging;                  /* push: the NEIGHBOUR's receive block (peer memory); unpack: mine */
+	unsigned int *block_counter;    /* push only: blocks of this launch that are done (local) */
+	unsigned int *sync_count;       /* push: syncs of this kind I have pushed on this face; wait: syncs I have
+	                                   pulled.  DEVICE-resident, so a replayed CUDA graph keeps counting */
+	volatile unsigned int *flag;    /* push: the neighbour's flag word; wait: mine */
 	long long dd_stride;
 	int origin[3], size[3];         /* rect in the sub-domain */
 	int ss[2];                      /* sub-domain Sx, Sy */
@@ -808,52 +922,106 @@ __device__ __forceinline__ void halo_copy(const HaloFace &F, bool to_staging)
 	}
 }
 
-/* push: both faces of one axis in ONE launch (blockIdx.y = face).  Packs the face and stores it
- * straight into the neighbour's receive block over NVLink; the last block of a face raises the
- * neighbour's flag.  ONE thread per block fences (system scope, cumulative over the block's peer
- * stores it observed through the barrier): a fence of scope >= cluster invalidates the SM's L1
- * (CCTL.IVALL), which the step kernel running next to this one depends on. */
-template <typename T>
-__global__ void halo_push_kernel(const HaloAxis A, unsigned int seq)
+/* last block of a face: everything this launch stored into the neighbour's block is visible before
+ * the neighbour sees the new sequence number */
+__device__ __forceinline__ void halo_publish(const HaloFace &F)
 {
-	const HaloFace &F = A.f[blockIdx.y];
-	if (F.vec == 4) halo_copy<T, sizeof(T) == 4 ? 4 : 2>(F, true);
-	else if (F.vec == 2) halo_copy<T, 2>(F, true);
-	else halo_copy<T, 1>(F, true);
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		__threadfence_system();
 		const unsigned int done = atomicAdd(F.block_counter, 1u);
 		if (done == gridDim.x - 1) {
 			*F.block_counter = 0;                 /* ready for the next push of this face */
+			const unsigned int seq = *F.sync_count + 1u;
+			*F.sync_count = seq;
 			__threadfence_system();
 			*F.flag = seq;
 		}
 	}
 }
 
-/* pull: both faces of one axis in ONE launch.  Every block waits (one thread spins, acquire at
- * system scope) until the neighbour's push has raised my flag, then unpacks my receive block. */
+/* push: both faces of one axis in ONE launch (blockIdx.y = face).  Packs the face and stores it
+ * straight into the neighbour's receive block over NVLink; the last block of a face raises the
+ * neighbour's flag.  ONE thread per block fences (system scope, cumulative over the block's peer
+ * stores it observed through the barrier): a fence of scope >= cluster invalidates the SM's L1
+ * (CCTL.IVALL), which the step kernel running next to this one depends on. */
 template <typename T>
-__global__ void halo_pull_kernel(const HaloAxis A, unsigned int seq)
+__global__ void halo_push_kernel(const HaloAxis A)
 {
 	const HaloFace &F = A.f[blockIdx.y];
-	if (threadIdx.x == 0) {
-		/* sequence numbers only grow; signed distance tolerates wrap-around */
-		while ((int)(*F.flag - seq) < 0) { __nanosleep(32); }
-		__threadfence_system();
+	if (F.vec == 4) halo_copy<T, sizeof(T) == 4 ? 4 : 2>(F, true);
+	else if (F.vec == 2) halo_copy<T, 2>(F, true);
+	else halo_copy<T, 1>(F, true);
+	halo_publish(F);
+}
+
+/* x faces whose bulk went out of the step kernels (XPUSH): the rim pass.  The cells of an x face that lie
+ * in the two outermost layers of y or z hold values the y/z phases of THIS sync delivered (edge
+ * populations on their way to the diagonal neighbour) or are ghost cells the step kernel skipped; they
+ * are re-read from dd -- final by now: this kernel runs behind the step kernels and the y/z unpack -- and
+ * stored over whatever the step kernel sent for them.  Then the flag goes up.  F.origin[0] = column. */
+template <typename T>
+__global__ void halo_xrim_flag_kernel(const HaloAxis A)
+{
+	const HaloFace &F = A.f[blockIdx.y];
+	const int sy = F.size[1], sz = F.size[2];
+	const unsigned int line_cells = 4u * (unsigned int)(sy + sz);
+	const unsigned int total = line_cells * (unsigned int)F.ncomp;
+	const T *dd = (const T *)F.dd;
+	T *st = (T *)F.staging;
+	for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		const unsigned int c = t / line_cells, q = t - c * line_cells;
+		int y, z;
+		if (q < 4u * (unsigned int)sz) {                       /* rows y = 0, 1, sy-2, sy-1 */
+			const int w = (int)(q / (unsigned int)sz); z = (int)(q - (unsigned int)w * sz);
+			y = w < 2 ? w : sy - 4 + w;
+		} else {                                               /* rows z = 0, 1, sz-2, sz-1 */
+			const unsigned int r = q - 4u * (unsigned int)sz;
+			const int w = (int)(r / (unsigned int)sy); y = (int)(r - (unsigned int)w * sy);
+			z = w < 2 ? w : sz - 4 + w;
+		}
+		if (y < 0 || y >= sy || z < 0 || z >= sz) continue;    /* faces thinner than 4 */
+		const long long face = (long long)z * sy + y;
+		st[(long long)F.st_comp[c] * sy * sz + face] =
+			dd[(long long)F.dd_comp[c] * F.dd_stride + F.origin[0] + (long long)y * F.ss[0] + (long long)z * F.ss[0] * F.ss[1]];
 	}
-	__syncthreads();
+	halo_publish(F);
+}
+
+/* wait: ONE thread per face (not a grid of spinning blocks next to the step kernel) waits until the
+ * neighbour's push has raised my flag to the next sequence number (acquire at system scope).  The
+ * expected number is counted in device memory.  A neighbour that never arrives (crashed rank) must
+ * not hang the GPU: after timeout_ns the wait gives up and leaves a mark the host finds in lbmWait. */
+__global__ void halo_wait_kernel(const HaloAxis A, int nfaces, unsigned long long timeout_ns, unsigned int *error_word)
+{
+	if ((int)threadIdx.x >= nfaces) return;
+	const HaloFace &F = A.f[threadIdx.x];
+	const unsigned int seq = *F.sync_count + 1u;
+	*F.sync_count = seq;
+	unsigned long long t0 = 0;
+	unsigned int spins = 0;
+	/* sequence numbers only grow; signed distance tolerates wrap-around */
+	while ((int)(*F.flag - seq) < 0) {
+		__nanosleep(40);
+		if ((++spins & 1023u) == 0) {
+			unsigned long long now;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			if (t0 == 0) t0 = now;
+			else if (now - t0 > timeout_ns) { atomicExch(error_word, 1u + threadIdx.x + 2u * blockIdx.x); break; }
+		}
+	}
+	__threadfence_system();
+}
+
+/* unpack: my receive block(s) of one axis -> the dd rects; runs behind halo_wait_kernel in stream
+ * order, so nothing spins here */
+template <typename T>
+__global__ void halo_unpack_kernel(const HaloAxis A)
+{
+	const HaloFace &F = A.f[blockIdx.y];
 	if (F.vec == 4) halo_copy<T, sizeof(T) == 4 ? 4 : 2>(F, false);
 	else if (F.vec == 2) halo_copy<T, 2>(F, false);
 	else halo_copy<T, 1>(F, false);
-}
-
-/* standalone wait, for transports that unpack with lbmHaloUnpack */
-__global__ void halo_wait_kernel(volatile unsigned int *flag, unsigned int seq)
-{
-	while ((int)(*flag - seq) < 0) { __nanosleep(64); }
-	__threadfence_system();
 }
 
 /* ================================================================== checksum
