@@ -33,6 +33,19 @@ CS = 0.1
 BYTES_PER_LUP_F32 = 2 * 19 * 4 + 4      # 156 B fp32, 308 B fp64
 
 
+PRESETS = {
+    "1": dict(size=256, scaling="weak", decomp="slab", dtype="f32"),
+    "2": dict(size=512, scaling="strong", decomp="slab", dtype="f32"),
+    "3-slab": dict(size=512, scaling="weak", decomp="slab", dtype="f32"),
+    "3-block": dict(size=512, scaling="weak", decomp="block", dtype="f32"),
+    "3-pencil": dict(size=512, scaling="weak", decomp="pencil", dtype="f32"),
+    "4": dict(size=384, scaling="strong", decomp="slab", dtype="f64"),
+    # /root/reference/benchmark.py:62-83 (weak: x = 1024 n, y = 1024, z = 32, -X n) and :107-129 (strong 1024x1024x32)
+    "recipe-weak": dict(size=1024, scaling="weak", decomp="slab-x", dtype="f32", shape=(1024, 1024, 32)),
+    "recipe-strong": dict(size=1024, scaling="strong", decomp="slab-x", dtype="f32", shape=(1024, 1024, 32)),
+}
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -139,16 +152,17 @@ def decomposition(n_gpus, decomp):
     return (1, 1, n_gpus)
 
 
-def scenario(n_gpus, size=SIZE, scaling="weak", decomp="slab", cs=CS):
+def scenario(n_gpus, size=SIZE, scaling="weak", decomp="slab", cs=CS, shape=None):
     from turbulent_lbm_multigpu_b200.configuration import CConfiguration
     cfg = CConfiguration()
     nums = decomposition(n_gpus, decomp)
+    base = tuple(shape) if shape else (size, size, size)
     if scaling == "weak":
-        cfg.domain_size = tuple(size * k for k in nums)
+        cfg.domain_size = tuple(b * k for b, k in zip(base, nums))
         # weak scaling keeps the cell length (hence tau, u_lid) constant: benchmark.py:72
         cfg.domain_length = tuple(0.1 * k for k in nums)
     else:
-        cfg.domain_size = (size, size, size)
+        cfg.domain_size = base
         cfg.domain_length = (0.1, 0.1, 0.1)
     cfg.subdomain_num = nums
     cfg.smagorinsky_constant = cs
@@ -245,16 +259,18 @@ def run_reference(args):
 
 
 def workload_config(args, n):
-    cfg = scenario(n, args.size, args.scaling, args.decomp, args.cs)
+    cfg = scenario(n, args.size, args.scaling, args.decomp, args.cs, getattr(args, "shape", None))
     sub = [d // k for d, k in zip(cfg.domain_size, cfg.subdomain_num)]
     elem = 4 if args.dtype == "f32" else 8
     ws = (19 * elem + 4) * sub[0] * sub[1] * sub[2] / 1e9
     tag = {(256, "weak", "f32"): " (BASELINE configs[1])", (512, "strong", "f32"): " (BASELINE configs[2])",
            (512, "weak", "f32"): " (BASELINE configs[3])", (384, "strong", "f64"): " (BASELINE configs[4])"}
-    return {"workload": "lid-driven cavity %d^3 %s D3Q19 %s %s%s" % (
-                args.size, "per GPU" if args.scaling == "weak" else "global", "fp32" if args.dtype == "f32" else "fp64",
+    shape = getattr(args, "shape", None)
+    return {"workload": "lid-driven cavity %s %s D3Q19 %s %s%s" % (
+                ("%dx%dx%d" % tuple(shape)) if shape else ("%d^3" % args.size),
+                "per GPU" if args.scaling == "weak" else "global", "fp32" if args.dtype == "f32" else "fp64",
                 ("Smagorinsky C_s=%g" % args.cs) if args.cs else "BGK",
-                tag.get((args.size, args.scaling, args.dtype), "")),
+                " (reference benchmark.py recipe)" if shape else tag.get((args.size, args.scaling, args.dtype), "")),
             "global_domain": list(cfg.domain_size), "subdomain_num": list(cfg.subdomain_num),
             "subdomain_size": sub,
             "parallelism": ("%s domain decomposition, 1 process per GPU" % args.decomp) if n > 1 else "single GPU",
@@ -285,7 +301,7 @@ def run_gpu(args):
     np_dtype = np.float32 if args.dtype == "f32" else np.float64
     elem = np.dtype(np_dtype).itemsize
     bytes_per_lup = 2 * 19 * elem + 4           # 156 B fp32, 308 B fp64
-    cfg = scenario(n, args.size, args.scaling, args.decomp, args.cs)
+    cfg = scenario(n, args.size, args.scaling, args.decomp, args.cs, getattr(args, "shape", None))
     domain = CDomain(-1, cfg.domain_size, (0, 0, 0), cfg.domain_length)
     backend = TorchDistributedBackend() if world > 1 else None
     # the library launches on torch-owned streams so that NCCL (torch.distributed) and a
@@ -296,7 +312,7 @@ def run_gpu(args):
         axis_order = "zyx" if cfg.subdomain_num[0] > 1 else "xyz"
     mgr = CManager(domain, cfg.subdomain_num, backend=backend, device=local, config=cfg,
                    sync_mode=args.sync if world > 1 else "host", dtype=np_dtype, axis_order=axis_order,
-                   store_velocity=False, store_density=False,
+                   store_velocity=args.store, store_density=args.store,
                    compute_stream=compute_stream.cuda_stream, comm_stream=comm_stream.cuda_stream)
     mgr.initSimulation(rank)
     ctrl = mgr.getController()
@@ -495,7 +511,20 @@ def main():
                     help="phase order of the halo sync (p2p): xyz = the reference's; zyx = x faces exchanged after "
                          "the interior kernel, no x shell; auto = zyx when the decomposition cuts x")
     ap.add_argument("--graph", action="store_true", help="capture the 2-step cycle in a CUDA graph")
+    ap.add_argument("--config", default=None, choices=sorted(PRESETS),
+                    help="BASELINE.json configs[] presets: 1 = 256^3/GPU weak z-slabs fp32 (the default), 2 = 512^3 strong, "
+                         "3-slab / 3-block / 3-pencil = 512^3/GPU weak, 4 = 384^3 fp64 strong, "
+                         "recipe-weak / recipe-strong = the reference's benchmark.py shapes (1024 n x 1024 x 32, -X n)")
+    ap.add_argument("--min-seconds", type=float, default=0.0,
+                    help="raise --steps until the timed region lasts at least this long (sustained-clock record)")
+    ap.add_argument("--no-verify", action="store_true",
+                    help="skip the parity leg (a small run of the same decomposition / transport / kernels checked "
+                         "bit for bit against the CPU oracle; its verdict is the `parity` key of the JSON line)")
+    ap.add_argument("--store", action="store_true", help="STORE_VELOCITY/STORE_DENSITY instantiations (visualisation/validate builds)")
     args = ap.parse_args()
+    if args.config:
+        for k, v in PRESETS[args.config].items():
+            setattr(args, k, v)
     # The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner
     # under NCCL_DEBUG=VERSION, OpenMP/torch warnings): keep the real stdout for the result line and
     # point file descriptor 1 at stderr for everything else.

@@ -47,6 +47,19 @@ def test_ini_averaging(tmp_path):
     assert abs(res[1]["ROOFLINE_FRAC_PER_GPU"] - 105.0 * 156.0 / 1e3 / 1000.0) < 1e-12
 
 
+def test_visualize_writes_results_txt_and_plots(tmp_path):
+    """reference benchmark.py:131-185: pretty-printed results and one plot per key plus the speed-up."""
+    res = {1: {"SECONDS": 2.0, "MLUPS": 100.0, "FPS": 5.0}, 2: {"SECONDS": 1.0, "MLUPS": 200.0, "FPS": 10.0},
+           4: {"SECONDS": 0.5, "MLUPS": 390.0, "FPS": 20.0}}
+    files = bm.visualize(res, str(tmp_path))
+    names = sorted(os.path.basename(f) for f in files)
+    assert names == ["plot_FPS.svg", "plot_MLUPS.svg", "plot_SECONDS.svg", "plot_speedup.svg"]
+    txt = (tmp_path / "results.txt").read_text()
+    assert "profiling results pretty print" in txt and "390.0" in txt
+    svg = (tmp_path / "plot_speedup.svg").read_text()
+    assert svg.startswith("<svg") and "Speedup Scaling" in svg and svg.count("<path") == 3
+
+
 def test_bench_reference_arm_prints_exactly_one_json_line():
     """bench.py's contract: ONE JSON line on stdout (libraries that print there are redirected to
     stderr), the reference arm's extra keys, and -- under torchrun with N > 1 -- ranks other than 0

@@ -113,6 +113,10 @@ def test_zyx_axis_order_x_faces_after_the_interior(D, nums, steps, overlap):
     ((40, 24, 48), (1, 1, 3), 30),       # a rank with two faces
     ((48, 40, 24), (2, 2, 2), 41),       # blocks (x cut: z,y,x order chosen like bench.py does)
     ((80, 24, 16), (2, 1, 1), 30),       # the reference's x split
+    ((512, 12, 10), (2, 1, 1), 21),      # rows of 256 cells = whole blocks: the block-uniform lane test of the fused x exchange
+    ((512, 24, 12), (2, 2, 1), 20),
+    ((1024, 10, 8), (2, 1, 1), 11),      # two blocks per row
+    ((120, 24, 16), (3, 1, 1), 21),      # a rank with two x faces
 ])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("cs", [0.0, 0.1])
@@ -150,6 +154,25 @@ def test_bench_defaults_decomposed_equal_oracle(D, nums, steps, dtype, cs):
         o = validation_sub_origin(r, nums, inner)
         s = ctrl.getSolver()
         assert bits_equal(s.storeVelocity(origin=(1, 1, 1), size=inner), single.storeVelocity(origin=o, size=inner)), (r, "velocity")
+
+
+@pytest.mark.parametrize("D,nums", [((80, 24, 16), (2, 1, 1)), ((48, 40, 24), (2, 2, 2))])
+def test_fused_x_exchange_materialises_on_host_access(D, nums):
+    """With the z,y,x order the x faces are received into their blocks and read from there by the next
+    step kernel; a host read of the populations in between (any step parity) must still see them in dd, and
+    the run must continue unharmed."""
+    L = (0.1, 0.1, 0.1)
+    cfg = _cfg()
+    cfg.smagorinsky_constant = 0.1
+    sim = InProcessSimulation(CDomain(-1, D, (0, 0, 0), L), nums, transport="p2p", overlap=True, config=cfg,
+                              dtype=np.float32, axis_order="zyx")
+    make, po = omulti.make_oracle_factory(D, nums, L, dtype=np.float32, variant=0, smagorinsky_cs=0.1)
+    md = omulti.MultiDomain(D, nums, make, slots="minimal", axis_order=(2, 1, 0))
+    for chunk in (7, 1, 2, 5):
+        sim.run(chunk)
+        md.run(chunk)
+        for r, ctrl in enumerate(sim.controllers):
+            assert bits_equal(ctrl.getSolver().storeDensityDistribution(), md.ranks[r]["solver"].dd), (r, chunk)
 
 
 def _device_count():

@@ -98,6 +98,63 @@ def analyse(filenames, bytes_per_lup=156.0, peak_gbs=None):
     return res
 
 
+def _svg_plot(path, title, xlabel, ylabel, xs, ys):
+    """One line plot as a dependency-free SVG (matplotlib is not part of the B200 image)."""
+    W, H, L, R, T, B = 640, 420, 80, 20, 40, 50
+    x0, x1 = min(xs) - 1, max(xs) + 1
+    y0, y1 = min(0.0, min(ys)), max(ys) * 1.08 if max(ys) > 0 else 1.0
+
+    def px(x):
+        return L + (x - x0) / (x1 - x0) * (W - L - R)
+
+    def py(y):
+        return H - B - (y - y0) / (y1 - y0) * (H - T - B)
+    out = ['<svg xmlns="http://www.w3.org/2000/svg" width="%d" height="%d" font-family="sans-serif" font-size="12">' % (W, H),
+           '<rect width="100%" height="100%" fill="white"/>',
+           '<text x="%d" y="22" text-anchor="middle" font-size="15">%s</text>' % (W // 2, title),
+           '<text x="%d" y="%d" text-anchor="middle">%s</text>' % (W // 2, H - 10, xlabel),
+           '<text x="16" y="%d" text-anchor="middle" transform="rotate(-90 16 %d)">%s</text>' % (H // 2, H // 2, ylabel)]
+    for k in range(6):
+        y = y0 + (y1 - y0) * k / 5
+        out.append('<line x1="%d" y1="%.1f" x2="%d" y2="%.1f" stroke="#ccc"/>' % (L, py(y), W - R, py(y)))
+        out.append('<text x="%d" y="%.1f" text-anchor="end">%.4g</text>' % (L - 6, py(y) + 4, y))
+    for x in xs:
+        out.append('<line x1="%.1f" y1="%d" x2="%.1f" y2="%d" stroke="#ccc"/>' % (px(x), T, px(x), H - B))
+        out.append('<text x="%.1f" y="%d" text-anchor="middle">%d</text>' % (px(x), H - B + 16, x))
+    pts = " ".join("%.1f,%.1f" % (px(x), py(y)) for x, y in zip(xs, ys))
+    out.append('<polyline points="%s" fill="none" stroke="green" stroke-dasharray="6,4" stroke-width="2"/>' % pts)
+    for x, y in zip(xs, ys):
+        out.append('<path d="M %.1f %.1f l 6 10 l -12 0 z" fill="green"/>' % (px(x), py(y) - 6))
+    out.append("</svg>")
+    with open(path, "w") as f:
+        f.write("\n".join(out))
+
+
+def visualize(res, outdir=INI_FILE_DIR):
+    """reference benchmark.py:131-185: pretty-print the averaged results (-> results.txt), one
+    '<KEY> scaling' plot per key over the number of GPUs and a speed-up plot (SECONDS[first] / SECONDS)."""
+    import pprint
+    os.makedirs(outdir, exist_ok=True)
+    with open(os.path.join(outdir, "results.txt"), "w") as f:
+        f.write("profiling results pretty print:\n" + pprint.pformat(res, indent=4) + "\n")
+    ngpus = sorted(res)
+    if not ngpus:
+        return []
+    files = []
+    for key in KEYS:
+        if not all(key in res[n] for n in ngpus):
+            continue
+        fn = os.path.join(outdir, "plot_%s.svg" % key)
+        _svg_plot(fn, key + " scaling", "# GPUs", key, ngpus, [float(res[n][key]) for n in ngpus])
+        files.append(fn)
+    if all("SECONDS" in res[n] for n in ngpus):
+        t = [float(res[n]["SECONDS"]) for n in ngpus]
+        fn = os.path.join(outdir, "plot_speedup.svg")
+        _svg_plot(fn, "Speedup Scaling", "# GPUs", "speedup", ngpus, [t[0] / v for v in t])
+        files.append(fn)
+    return files
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -131,6 +188,8 @@ def main(argv=None):
                   bytes_per_lup=308.0 if a.double else 156.0, peak_gbs=measured_peak())
     with open("results.json", "w") as f:
         json.dump(res, f, indent=1, sort_keys=True)
+    for fn in visualize(res):
+        print("saved graph:", fn)
     for nproc in sorted(res):
         r = res[nproc]
         print("np %2d  MLUPS %10.1f  speed-up %5.2f  efficiency %5.1f %%  roofline/GPU %s" % (

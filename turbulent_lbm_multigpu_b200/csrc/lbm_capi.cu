@@ -47,7 +47,9 @@ struct lbm_solver {
 	lbm_desc desc;
 	std::vector<lbm_face> faces;
 	int axis_order;              /* LBM_AXIS_ORDER_*: phase order of a sync */
-	int x_in_kernel;             /* 1 + sync kind whose x faces the last step kernels pushed themselves (XPUSH), 0 = none */
+	int x_in_kernel;             /* 1 + sync kind whose x faces the last step kernels pushed themselves (XFUSE), 0 = none */
+	int x_pending;               /* 1 + sync kind whose x faces were received but not scattered into dd: the next
+	                                XFUSE step reads them out of the receive block; anything else flushes first */
 	int xfuse;                   /* fused x push allowed (LBM_B200_XFUSE=0 turns it off) */
 	unsigned int *d_error;       /* device word: a halo wait gave up (neighbour never arrived) */
 	unsigned long long wait_timeout_ns;
@@ -141,6 +143,7 @@ struct LaunchScope {
 };
 
 uint32_t popcount19(uint32_t m);
+int flush_x_pending(lbm_t h, cudaStream_t s);
 
 /* fused x push: only with the z,y,x phase order, the 5-slot payload and every x face connected */
 bool x_fusable(lbm_t h)
@@ -157,16 +160,23 @@ bool x_fusable(lbm_t h)
 }
 
 template <typename T>
-StepParams<T> make_params(lbm_t h, const Box &b, bool alpha, bool xpush)
+StepParams<T> make_params(lbm_t h, const Box &b, bool alpha, bool xfuse)
 {
 	StepParams<T> P;
 	P.xstage[0] = P.xstage[1] = NULL;
+	P.xpull[0] = P.xpull[1] = NULL;
 	P.xface_n = (long long)h->sy * h->sz;
-	if (xpush) {
-		const int kind = alpha ? LBM_SYNC_ALPHA : LBM_SYNC_BETA;
+	const int cells_per_block = h->block * h->vec;
+	P.bpr = (b.nx == h->sx && b.x0 == 0 && h->sx % cells_per_block == 0) ? h->sx / cells_per_block : 0;
+	if (xfuse) {
+		const int kind = alpha ? LBM_SYNC_ALPHA : LBM_SYNC_BETA;          /* the sync this step feeds */
+		const int consumed = alpha ? LBM_SYNC_BETA : LBM_SYNC_ALPHA;      /* the sync this step consumes */
 		for (size_t i = 0; i < h->faces.size(); i++) {
 			const lbm_face &f = h->faces[i];
-			if (f.axis == 0) P.xstage[f.dir[0] > 0 ? 0 : 1] = (T *)(f.peer_block + f.peer_stage_off[kind]);
+			if (f.axis != 0) continue;
+			const int side = f.dir[0] > 0 ? 0 : 1;
+			P.xstage[side] = (T *)(f.peer_block + f.peer_stage_off[kind]);
+			if (h->x_pending == 1 + consumed) P.xpull[side] = (const T *)(f.local_block + f.stage_off[consumed]);
 		}
 	}
 	P.dd = (T *)h->dd; P.flags = h->flags; P.velocity = (T *)h->velocity; P.density = (T *)h->density;
@@ -264,6 +274,9 @@ int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream
 int launch_step(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream_t sg = NULL, bool xpush = false)
 {
 	if (!sg) sg = s;
+	/* a lazily pulled x face is consumed by the XFUSE step of the matching parity; anything else needs it in dd */
+	if (h->x_pending && (!xpush || h->x_pending != 1 + (alpha ? LBM_SYNC_BETA : LBM_SYNC_ALPHA)))
+		if (int rc = flush_x_pending(h, s)) return rc;
 	if (h->dtype == LBM_F32) {
 		switch (h->vec) {
 		case 4: return launch_step_tv<float, 4>(h, alpha, b, s, sg, xpush);
@@ -512,7 +525,7 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	h->profile_mode = 0; h->prof_base = NULL; h->prof_dropped = 0;
 	h->xshell = 32;
 	if (const char *e = getenv("LBM_B200_XSHELL")) h->xshell = atoi(e) > 1 ? atoi(e) : 2;
-	h->x_in_kernel = 0; h->d_error = NULL;
+	h->x_in_kernel = 0; h->x_pending = 0; h->d_error = NULL;
 	h->xfuse = 1;
 	if (const char *e = getenv("LBM_B200_XFUSE")) h->xfuse = atoi(e) != 0;
 	h->wait_timeout_ns = 30ull * 1000000000ull;
@@ -604,6 +617,7 @@ int lbmReset(lbm_t h)
 	CHECK_HANDLE(h);
 	if (int rc = use_device(h)) return rc;
 	h->counter = 0;
+	h->x_in_kernel = 0; h->x_pending = 0;
 	const int block = 256;
 	const unsigned grid = (unsigned)((h->n + block - 1) / block);
 	const int *bc = h->desc.bc;
@@ -695,6 +709,7 @@ int lbmStepInterior(lbm_t h, int ghost_faces)
 	const bool xpush = (ghost_faces & 3) == 0 && x_fusable(h);
 	if (int rc = launch_step(h, alpha, interior, h->compute, h->step_aux, xpush)) return rc;
 	h->x_in_kernel = xpush ? 1 + (alpha ? LBM_SYNC_ALPHA : LBM_SYNC_BETA) : 0;
+	h->x_pending = 0;            /* consumed by the shell + interior kernels just launched (or flushed) */
 	h->counter++;
 	return LBM_OK;
 }
@@ -753,12 +768,16 @@ int lbmSetDrivenCavityVelocity(lbm_t h, double u_lid) { CHECK_HANDLE(h); h->u_li
 int lbmStoreDD(lbm_t h, void *host_dst, const int origin[3], const int size[3])
 {
 	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	if (int rc = flush_x_pending(h, h->compute)) return rc;
 	return store_field(h, h->dd, h->elem, 19, host_dst, origin, size, h->stride);
 }
 
 int lbmSetDD(lbm_t h, const void *host_src, const int origin[3], const int size[3], const int norm[3])
 {
 	CHECK_HANDLE(h);
+	if (int rc = use_device(h)) return rc;
+	if (int rc = flush_x_pending(h, h->compute)) return rc;
 	int keep[19];
 	for (int f = 0; f < 19; f++)   /* src/CLbmSolver.hpp:748: norm.dotProd(lbm_units[f]) > 0 */
 		keep[f] = !norm || (norm[0] * kUnits[f][0] + norm[1] * kUnits[f][1] + norm[2] * kUnits[f][2] > 0);
@@ -879,6 +898,7 @@ int lbmHaloPack(lbm_t h, const int origin[3], const int size[3], uint32_t slot_m
 	if (!origin || !size || !dev_buf) return fail(h, LBM_ERR_INVALID, "null argument");
 	if (int rc = use_device(h)) return rc;
 	if (int rc = check_rect(h, origin, size)) return rc;
+	if (int rc = flush_x_pending(h, stream ? (cudaStream_t)stream : h->comm)) return rc;
 	int field[19], packed[19], n = 0;
 	for (int f = 0; f < 19; f++) if ((slot_mask >> f) & 1) { field[n] = f; packed[n] = n; n++; }
 	if (n == 0) return LBM_OK;
@@ -896,6 +916,7 @@ int lbmHaloUnpack(lbm_t h, const int origin[3], const int size[3], uint32_t buf_
 	if (write_mask & ~buf_slot_mask) return fail(h, LBM_ERR_INVALID, "write_mask selects slots the buffer does not hold");
 	if (int rc = use_device(h)) return rc;
 	if (int rc = check_rect(h, origin, size)) return rc;
+	if (int rc = flush_x_pending(h, stream ? (cudaStream_t)stream : h->comm)) return rc;
 	int field[19], packed[19], n = 0, pos = 0;
 	for (int f = 0; f < 19; f++) {
 		if (!((buf_slot_mask >> f) & 1)) continue;
@@ -918,6 +939,8 @@ int lbmHaloCopyPeer(lbm_t src, const int src_origin[3], lbm_t dst, const int dst
 	if (int rc = use_device(src)) return rc;
 	if (int rc = check_rect(src, src_origin, size)) return rc;
 	if (int rc = check_rect(dst, dst_origin, size)) return fail(src, rc, dst->error);
+	if (int rc = flush_x_pending(src, stream ? (cudaStream_t)stream : src->comm)) return rc;
+	if (dst->x_pending) { if (int rc = use_device(dst)) return rc; if (int rc = flush_x_pending(dst, dst->compute)) return rc; if (int rc = use_device(src)) return rc; }
 	if (src->device != dst->device) {
 		int can = 0;
 		CUDA_TRY(src, cudaDeviceCanAccessPeer(&can, src->device, dst->device));
@@ -943,6 +966,7 @@ int lbmHaloCopyPeer(lbm_t src, const int src_origin[3], lbm_t dst, const int dst
 }
 
 /* ---------------------------------------------------------------- peer-memory halo exchange */
+} /* extern "C" */
 namespace {
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -987,13 +1011,11 @@ unsigned face_blocks(const HaloFace &F, bool exposed)
 	return (unsigned)(g < 1 ? 1 : g);
 }
 
-/* every face of one axis in ONE launch.  rim_only: the bulk of the (x) faces already left the step
- * kernels (XPUSH); send the rim lines and raise the flags. */
-int axis_push(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed, bool rim_only)
+/* descriptors of the faces of one axis, push side (my dd rect -> the neighbour's receive block) */
+int build_push(lbm_t h, int kind, int axis, HaloAxis &A, unsigned &nf, unsigned &blocks, bool exposed)
 {
-	HaloAxis A;
 	memset(&A, 0, sizeof(A));
-	unsigned nf = 0, blocks = 1;
+	nf = 0; blocks = 1;
 	for (size_t i = 0; i < h->faces.size(); i++) {
 		lbm_face &f = h->faces[i];
 		if (f.axis != axis) continue;
@@ -1008,37 +1030,18 @@ int axis_push(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed, bool ri
 		F.flag = (volatile unsigned int *)(f.peer_block + 64 * kind);
 		F.sync_count = f.counters + kind;
 		F.block_counter = f.counters + 4;
-		unsigned b = face_blocks(F, exposed);
-		if (rim_only) {
-			const long long work = 4LL * (F.size[1] + F.size[2]) * F.ncomp;
-			b = (unsigned)((work + 255) / 256);
-			if (b > 148) b = 148;
-			if (b < 1) b = 1;
-		}
+		const unsigned b = face_blocks(F, exposed);
 		if (b > blocks) blocks = b;
 		nf++;
 	}
-	if (nf == 0) return LBM_OK;
-	dim3 grid(blocks, nf);
-	if (rim_only) {
-		LaunchScope ls(h, "halo_xrim", s);
-		if (h->dtype == LBM_F32) halo_xrim_flag_kernel<float><<<grid, 256, 0, s>>>(A);
-		else halo_xrim_flag_kernel<double><<<grid, 256, 0, s>>>(A);
-	} else {
-		LaunchScope ls(h, "halo_push", s);
-		if (h->dtype == LBM_F32) halo_push_kernel<float><<<grid, 256, 0, s>>>(A);
-		else halo_push_kernel<double><<<grid, 256, 0, s>>>(A);
-	}
-	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;
 }
 
-/* wait (one thread per face) + unpack, two launches in stream order */
-int axis_pull(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed)
+/* ... pull side (my receive block -> my dd rect) */
+int build_pull(lbm_t h, int kind, int axis, HaloAxis &A, unsigned &nf, unsigned &blocks, bool exposed)
 {
-	HaloAxis A;
 	memset(&A, 0, sizeof(A));
-	unsigned nf = 0, blocks = 1;
+	nf = 0; blocks = 1;
 	for (size_t i = 0; i < h->faces.size(); i++) {
 		lbm_face &f = h->faces[i];
 		if (f.axis != axis) continue;
@@ -1060,12 +1063,84 @@ int axis_pull(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed)
 		if (b > blocks) blocks = b;
 		nf++;
 	}
+	return LBM_OK;
+}
+
+unsigned rim_blocks(const HaloAxis &A, unsigned nf)
+{
+	unsigned blocks = 1;
+	for (unsigned i = 0; i < nf; i++) {
+		const long long work = 4LL * (A.f[i].size[1] + A.f[i].size[2]) * A.f[i].ncomp;
+		unsigned b = (unsigned)((work + 255) / 256);
+		if (b > 148) b = 148;
+		if (b > blocks) blocks = b;
+	}
+	return blocks;
+}
+
+int axis_unpack(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed)
+{
+	HaloAxis A; unsigned nf, blocks;
+	if (int rc = build_pull(h, kind, axis, A, nf, blocks, exposed)) return rc;
 	if (nf == 0) return LBM_OK;
+	dim3 grid(blocks, nf);
+	LaunchScope ls(h, "halo_pull", s);
+	if (h->dtype == LBM_F32) halo_unpack_kernel<float><<<grid, 256, 0, s>>>(A);
+	else halo_unpack_kernel<double><<<grid, 256, 0, s>>>(A);
+	CUDA_TRY(h, cudaGetLastError());
+	return LBM_OK;
+}
+
+/* an x face that was received but left in its receive block (lazy pull) is scattered into dd now */
+int flush_x_pending(lbm_t h, cudaStream_t s)
+{
+	if (!h->x_pending) return LBM_OK;
+	const int kind = h->x_pending - 1;
+	h->x_pending = 0;
+	return axis_unpack(h, kind, 0, s, true);
+}
+
+/* every face of one axis in ONE launch.  rim_only: the bulk of the (x) faces already left the step
+ * kernels (XFUSE); send the rim lines and raise the flags -- and, with_wait, wait for the neighbour's
+ * flags in the same launch. */
+int axis_push(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed, bool rim_only, bool with_wait = false)
+{
+	HaloAxis A; unsigned nf, blocks;
+	if (int rc = build_push(h, kind, axis, A, nf, blocks, exposed)) return rc;
+	if (nf == 0) return LBM_OK;
+	if (!rim_only) {
+		if (int rc = flush_x_pending(h, s)) return rc;      /* the face is read out of dd */
+		dim3 grid(blocks, nf);
+		LaunchScope ls(h, "halo_push", s);
+		if (h->dtype == LBM_F32) halo_push_kernel<float><<<grid, 256, 0, s>>>(A);
+		else halo_push_kernel<double><<<grid, 256, 0, s>>>(A);
+	} else {
+		HaloAxis W; unsigned nw = 0, wb;
+		if (with_wait) { if (int rc = build_pull(h, kind, axis, W, nw, wb, exposed)) return rc; }
+		else memset(&W, 0, sizeof(W));
+		dim3 grid(rim_blocks(A, nf), nf);
+		LaunchScope ls(h, "halo_xrim", s);
+		if (h->dtype == LBM_F32) halo_xrim_flag_kernel<float><<<grid, 256, 0, s>>>(A, W, (int)nw, h->wait_timeout_ns, h->d_error);
+		else halo_xrim_flag_kernel<double><<<grid, 256, 0, s>>>(A, W, (int)nw, h->wait_timeout_ns, h->d_error);
+	}
+	CUDA_TRY(h, cudaGetLastError());
+	return LBM_OK;
+}
+
+/* wait (one thread per face), then unpack -- or, lazy (x faces of an XFUSE run), leave the data in the
+ * receive block for the next step kernel to read */
+int axis_pull(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed, bool lazy = false)
+{
+	HaloAxis A; unsigned nf, blocks;
+	if (int rc = build_pull(h, kind, axis, A, nf, blocks, exposed)) return rc;
+	if (nf == 0) return LBM_OK;
+	if (axis == 0) { if (int rc = flush_x_pending(h, s)) return rc; }
 	{
 	LaunchScope ls(h, "halo_wait", s);
 	halo_wait_kernel<<<1, 32, 0, s>>>(A, (int)nf, h->wait_timeout_ns, h->d_error);
 	}
 	CUDA_TRY(h, cudaGetLastError());
+	if (lazy) { h->x_pending = 1 + kind; return LBM_OK; }
 	dim3 grid(blocks, nf);
 	{
 	LaunchScope ls(h, "halo_pull", s);
@@ -1087,6 +1162,7 @@ int ghost_mask_of_faces(lbm_t h)
 }
 
 } // namespace
+extern "C" {
 
 int lbmCommAddFace(lbm_t h, int dst_rank, const int send_origin[3], const int recv_origin[3], const int size[3],
 		const int dir[3], int slots, int *face_id)
@@ -1211,7 +1287,7 @@ int lbmCommPull(lbm_t h, int sync_kind, int axis)
 	CHECK_HANDLE(h);
 	if (sync_kind != LBM_SYNC_ALPHA && sync_kind != LBM_SYNC_BETA) return fail(h, LBM_ERR_INVALID, "bad sync kind");
 	if (int rc = use_device(h)) return rc;
-	return axis_pull(h, sync_kind, axis, h->comm, false);
+	return axis_pull(h, sync_kind, axis, h->comm, false, axis == 0 && x_fusable(h));
 }
 
 int lbmCommSetAxisOrder(lbm_t h, int order)
@@ -1280,9 +1356,17 @@ static int comm_step(lbm_t h, cudaEvent_t *marks /* NULL or 5 timing events */)
 		 * wait + unpack with the whole machine. */
 		if (int rc = lbmStreamWaitStream(h, 0)) return rc;
 		const bool rim_only = h->x_in_kernel == 1 + kind;
+		const bool lazy = x_fusable(h);
 		h->x_in_kernel = 0;
-		if (int rc = axis_push(h, kind, 0, h->compute, true, rim_only)) return rc;
-		if (int rc = axis_pull(h, kind, 0, h->compute, true)) return rc;
+		if (rim_only && lazy) {
+			/* the whole exposed x tail is ONE small kernel: rim lines, flag, wait for the neighbour's flag;
+			 * the received faces stay in their blocks for the next step kernels */
+			if (int rc = axis_push(h, kind, 0, h->compute, true, true, true)) return rc;
+			h->x_pending = 1 + kind;
+		} else {
+			if (int rc = axis_push(h, kind, 0, h->compute, true, rim_only)) return rc;
+			if (int rc = axis_pull(h, kind, 0, h->compute, true, lazy)) return rc;
+		}
 		if (marks) CUDA_TRY(h, cudaEventRecord(marks[3], h->compute));
 	}
 	if (marks) CUDA_TRY(h, cudaEventRecord(marks[4], h->compute));
@@ -1320,7 +1404,10 @@ int lbmGetDevicePointer(lbm_t h, int which, void **ptr, size_t *bytes)
 	if (!ptr) return fail(h, LBM_ERR_INVALID, "null ptr");
 	size_t b = 0;
 	switch (which) {
-	case LBM_BUF_DD: *ptr = h->dd; b = (size_t)19 * h->stride * h->elem; break;
+	case LBM_BUF_DD:
+		if (int rc = use_device(h)) return rc;
+		if (int rc = flush_x_pending(h, h->compute)) return rc;
+		*ptr = h->dd; b = (size_t)19 * h->stride * h->elem; break;
 	case LBM_BUF_FLAGS: *ptr = h->flags; b = (size_t)h->n * sizeof(int); break;
 	case LBM_BUF_VELOCITY: *ptr = h->velocity; b = h->velocity ? (size_t)3 * h->n * h->elem : 0; break;
 	case LBM_BUF_DENSITY: *ptr = h->density; b = h->density ? (size_t)h->n * h->elem : 0; break;

@@ -58,13 +58,20 @@ struct StepParams {
 	 * offset read from the constant bank: cheap to rematerialise for the push, which keeps 18
 	 * 64-bit pointers out of the register file between pull and push (see beta_uses_offset_table) */
 	long long boff[18];
-	/* fused x-face halo push (XPUSH instantiations; lbmCommStep with the z,y,x phase order): the
-	 * thread that owns the cell next to an x ghost face (x = 1 / x = sx-2) holds the 5 populations
-	 * the x neighbour consumes in registers and stores them straight into the neighbour's receive
-	 * block [position][z][y] (peer memory over NVLink) -- no strided gather kernel afterwards.
-	 * xstage[side] == NULL: that side has no neighbour. */
+	/* fused x-face halo exchange (XFUSE instantiations; lbmCommStep with the z,y,x phase order).
+	 * An x ghost column is one element per row: gathering / scattering it with separate kernels touches
+	 * one DRAM page per row and slot and costs 15 % of a 256^3 step.  Instead the thread that owns the
+	 * cell next to an x ghost face (x = 1 / x = sx-2)
+	 *   - PUSH: stores the 5 populations the x neighbour consumes, which it holds in registers, straight
+	 *     into the neighbour's receive block [position][z][y] (peer memory over NVLink);
+	 *   - PULL: takes the 5 populations it consumes from the neighbour out of MY receive block instead
+	 *     of the ghost column (beta) / its own slots (alpha), so the block is never scattered into dd
+	 *     on the step path (the host-side entry points materialise it on demand).
+	 * xstage[side] / xpull[side] == NULL: nothing to push / nothing pending on that side. */
 	T *xstage[2];
+	const T *xpull[2];
 	long long xface_n;       /* sy * sz: cells of an x face = stride between staging positions */
+	int bpr;                 /* > 0: full rows and sx is a multiple of the cells of a block -> blocks per row */
 };
 
 /* slots an x face ships, ascending = their position in the staging block.
@@ -478,21 +485,33 @@ __device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
 	return box_cell<T, VEC>(P, gid, off);
 }
 
-/* XPUSH: which element of this thread's VEC-wide group is the cell next to the low / high x ghost
- * face (-1: none), and the cell's index in the face [z][y].  off = offset of the group inside its plane. */
+/* XFUSE: which element of this thread's VEC-wide group is the cell next to the low / high x ghost
+ * face (-1: none), and the cell's index in the face [z][y].  off = offset of the group inside its plane.
+ * Cheap (block-uniform division) when rows are whole multiples of a block; re-evaluated at each use
+ * instead of being kept in registers across the collision (the volatile read of %ctaid defeats CSE). */
 template <typename T, int VEC>
-__device__ __forceinline__ void xpush_lanes(const StepParams<T> &P, long long off, int &e_lo, int &e_hi, long long &rowidx)
+__device__ __forceinline__ void xfuse_lanes(const StepParams<T> &P, long long off, int &e_lo, int &e_hi, long long &rowidx)
 {
-	const unsigned int po = (unsigned int)off;                 /* a plane has < 2^32 cells */
-	const unsigned int y = po / (unsigned int)P.sx;
-	const int x0 = (int)(po - y * (unsigned int)P.sx);
+	unsigned int y;
+	int x0;
+	if (P.bpr > 0) {
+		unsigned int bx;
+		asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
+		const unsigned int q = bx / (unsigned int)P.bpr;
+		y = (unsigned int)P.y0 + q;
+		x0 = (int)((bx - q * (unsigned int)P.bpr) * blockDim.x + threadIdx.x) * VEC;
+	} else {
+		const unsigned int po = (unsigned int)off;             /* a plane has < 2^32 cells */
+		y = po / (unsigned int)P.sx;
+		x0 = (int)(po - y * (unsigned int)P.sx);
+	}
 	rowidx = (long long)box_z(P) * P.sy + y;
-	e_lo = (P.xstage[0] != nullptr && x0 <= 1 && 1 < x0 + VEC) ? 1 - x0 : -1;
-	e_hi = (P.xstage[1] != nullptr && x0 <= P.sx - 2 && P.sx - 2 < x0 + VEC) ? P.sx - 2 - x0 : -1;
+	e_lo = (x0 <= 1 && 1 < x0 + VEC) ? 1 - x0 : -1;
+	e_hi = (x0 <= P.sx - 2 && P.sx - 2 < x0 + VEC) ? P.sx - 2 - x0 : -1;
 }
 
 /* ================================================================== ALPHA kernel */
-template <typename T, int VEC, bool SMAG, bool STORE, bool XPUSH>
+template <typename T, int VEC, bool SMAG, bool STORE, bool XFUSE>
 __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 {
 	long long gid, poff;
@@ -506,19 +525,49 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 	bool all_ghost = true;
 #pragma unroll
 	for (int e = 0; e < VEC; e++) all_ghost &= (flag[e] == FLAG_GHOST);
-	if (all_ghost) return;                       /* lbm_alpha.cl:31-32 */
-	if (!any_write && !STORE) {                  /* obstacle cells write nothing (:305-343) ... */
-		if (!XPUSH) return;
-		int e_lo, e_hi;                          /* ... but a cell next to an x face still ships its slots */
+	/* lbm_alpha.cl:31-32: ghost cells are skipped; obstacle cells write nothing (:305-343).  A group
+	 * that holds the cell next to an x face still pulls / ships that cell's slots. */
+	bool xlane = false;
+	if (XFUSE && (all_ghost || (!any_write && !STORE))) {
+		int e_lo, e_hi;
 		long long rowidx;
-		xpush_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
-		if (e_lo < 0 && e_hi < 0) return;
+		xfuse_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
+		xlane = (e_lo >= 0 && (P.xpull[0] || P.xstage[0])) || (e_hi >= 0 && (P.xpull[1] || P.xstage[1]));
 	}
+	if (all_ghost && !xlane) return;
+	if (!any_write && !STORE && !xlane) return;
 
 	T v[19][VEC];
 	T *base = P.dd + gid;
 #pragma unroll
 	for (int i = 0; i < 19; i++) VecIO<T, VEC>::load(base + (long long)i * P.ns, v[i]);
+
+	bool pulled = false;
+	if (XFUSE) {
+		/* PULL: what the x neighbour's beta step streamed into this cell sits in my receive block
+		 * (the reference's setDensityDistribution(..., norm) would have scattered it into these slots) */
+		int e_lo, e_hi;
+		long long rowidx;
+		xfuse_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
+		if (e_lo >= 0 && P.xpull[0]) {
+			const T *st = P.xpull[0] + rowidx;
+			pulled = true;
+#pragma unroll
+			for (int e = 0; e < VEC; e++) if (e == e_lo) {
+#pragma unroll
+				for (int k = 0; k < 5; k++) v[2 * k + (k ? 2 : 0)][e] = __ldcg(st + k * P.xface_n);     /* slots 0,4,6,8,10 */
+			}
+		}
+		if (e_hi >= 0 && P.xpull[1]) {
+			const T *st = P.xpull[1] + rowidx;
+			pulled = true;
+#pragma unroll
+			for (int e = 0; e < VEC; e++) if (e == e_hi) {
+#pragma unroll
+				for (int k = 0; k < 5; k++) v[2 * k + (k ? 3 : 1)][e] = __ldcg(st + k * P.xface_n);     /* slots 1,5,7,9,11 */
+			}
+		}
+	}
 
 	T orho[VEC], ovx[VEC], ovy[VEC], ovz[VEC];
 #pragma unroll
@@ -536,27 +585,31 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 #pragma unroll
 		for (int i = 0; i < 19; i++) v[i][e] = d[i];
 	}
-	if (any_write) {
+	/* `pulled`: a cell the step does not update (obstacle, ghost rim) keeps what it pulled in dd, as
+	 * if it had been unpacked there */
+	if (any_write || pulled) {
 #pragma unroll
 		for (int i = 0; i < 18; i++) VecIO<T, VEC>::store(base + (long long)i * P.ns, v[i ^ 1]);
 		VecIO<T, VEC>::store(base + 18LL * P.ns, v[18]);
 	}
-	if (XPUSH) {
-		/* slot j holds v[j^1] after this step.  Ghost cells (rims of the y/z faces) are left to the
-		 * rim pass that follows the y/z unpack (halo_xrim_flag_kernel).  (The lane test is evaluated
-		 * here, behind the stores, so that it occupies no registers across the collision.) */
+	if (XFUSE) {
+		/* PUSH: slot j holds v[j^1] after this step.  Ghost cells (rims of the y/z faces) are left to
+		 * the rim pass that follows the y/z unpack (halo_xrim_flag_kernel). */
 		int e_lo, e_hi;
 		long long rowidx;
-		xpush_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
+		xfuse_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
+		if (e_lo >= 0 && P.xstage[0]) {
+			T *st = P.xstage[0] + rowidx;
 #pragma unroll
-		for (int e = 0; e < VEC; e++) {
-			if (e == e_lo && flag[e] != FLAG_GHOST) {
-				T *st = P.xstage[0] + rowidx;
+			for (int e = 0; e < VEC; e++) if (e == e_lo && flag[e] != FLAG_GHOST) {
 #pragma unroll
 				for (int k = 0; k < 5; k++) st[k * P.xface_n] = v[2 * k + (k ? 3 : 1)][e];   /* slots 0,4,6,8,10 <- v[1,5,7,9,11] */
 			}
-			if (e == e_hi && flag[e] != FLAG_GHOST) {
-				T *st = P.xstage[1] + rowidx;
+		}
+		if (e_hi >= 0 && P.xstage[1]) {
+			T *st = P.xstage[1] + rowidx;
+#pragma unroll
+			for (int e = 0; e < VEC; e++) if (e == e_hi && flag[e] != FLAG_GHOST) {
 #pragma unroll
 				for (int k = 0; k < 5; k++) st[k * P.xface_n] = v[2 * k + (k ? 2 : 0)][e];   /* slots 1,5,7,9,11 <- v[0,4,6,8,10] */
 			}
@@ -615,7 +668,7 @@ __device__ __forceinline__ constexpr bool beta_uses_offset_table()
 	return LBM_BETA_OFFTAB == 1 || (LBM_BETA_OFFTAB == 2 && SMAG && !STORE && sizeof(T) == 4);
 }
 
-template <typename T, int VEC, bool SMAG, bool STORE, int ORDER, bool XPUSH>
+template <typename T, int VEC, bool SMAG, bool STORE, int ORDER, bool XFUSE>
 __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 {
 	long long gid, poff;
@@ -655,6 +708,38 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	}
 	VecIO<T, VEC>::load(base + 18LL * P.ns, v[18]);
 
+	if (XFUSE) {
+		/* PULL: location (slot j, c + e_j) in the ghost column next to the x = 1 (x = sx-2) cell holds
+		 * what the neighbour's alpha step left there -- it sits in my receive block at face index
+		 * row(c) + e_y + e_z * sy (in range: this path is a plane + a row away from the array ends);
+		 * it is read as d[j^1]. */
+		int e_lo, e_hi;
+		long long rowidx;
+		xfuse_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
+		if (e_lo >= 0 && P.xpull[0]) {
+			const T *st = P.xpull[0] + rowidx;
+#pragma unroll
+			for (int e = 0; e < VEC; e++) if (e == e_lo) {
+				v[0][e] = __ldcg(st);                              /* slot 1  (-1, 0, 0) */
+				v[4][e] = __ldcg(st + 1 * P.xface_n - 1);          /* slot 5  (-1,-1, 0) */
+				v[6][e] = __ldcg(st + 2 * P.xface_n + 1);          /* slot 7  (-1, 1, 0) */
+				v[8][e] = __ldcg(st + 3 * P.xface_n - P.sy);       /* slot 9  (-1, 0,-1) */
+				v[10][e] = __ldcg(st + 4 * P.xface_n + P.sy);      /* slot 11 (-1, 0, 1) */
+			}
+		}
+		if (e_hi >= 0 && P.xpull[1]) {
+			const T *st = P.xpull[1] + rowidx;
+#pragma unroll
+			for (int e = 0; e < VEC; e++) if (e == e_hi) {
+				v[1][e] = __ldcg(st);                              /* slot 0  ( 1, 0, 0) */
+				v[5][e] = __ldcg(st + 1 * P.xface_n + 1);          /* slot 4  ( 1, 1, 0) */
+				v[7][e] = __ldcg(st + 2 * P.xface_n - 1);          /* slot 6  ( 1,-1, 0) */
+				v[9][e] = __ldcg(st + 3 * P.xface_n + P.sy);       /* slot 8  ( 1, 0, 1) */
+				v[11][e] = __ldcg(st + 4 * P.xface_n - P.sy);      /* slot 10 ( 1, 0,-1) */
+			}
+		}
+	}
+
 	T orho[VEC], ovx[VEC], ovy[VEC], ovz[VEC];
 #pragma unroll
 	for (int e = 0; e < VEC; e++) {
@@ -673,25 +758,27 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	}
 	VecIO<T, VEC>::store(base + 18LL * P.ns, v[18]);
 
-	if (XPUSH) {
-		/* the x = 1 (x = sx-2) cell is the only writer of the e_x = -1 (+1) slots of the ghost column
-		 * next to it: location (slot j, c + e_j) has face index row(c) + e_y + e_z * sy.  Blocks on
-		 * this path are more than a plane + a row away from the array ends, so the index is in range. */
+	if (XFUSE) {
+		/* PUSH: the x = 1 (x = sx-2) cell is the only writer of the e_x = -1 (+1) slots of the ghost
+		 * column next to it; the same values go to the neighbour, same face index as above. */
 		int e_lo, e_hi;
 		long long rowidx;
-		xpush_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
+		xfuse_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
+		if (e_lo >= 0 && P.xstage[0]) {
+			T *st = P.xstage[0] + rowidx;
 #pragma unroll
-		for (int e = 0; e < VEC; e++) {
-			if (e == e_lo) {
-				T *st = P.xstage[0] + rowidx;
+			for (int e = 0; e < VEC; e++) if (e == e_lo) {
 				st[0] = v[1][e];                               /* (-1, 0, 0) */
 				st[1 * P.xface_n - 1] = v[5][e];               /* (-1,-1, 0) */
 				st[2 * P.xface_n + 1] = v[7][e];               /* (-1, 1, 0) */
 				st[3 * P.xface_n - P.sy] = v[9][e];            /* (-1, 0,-1) */
 				st[4 * P.xface_n + P.sy] = v[11][e];           /* (-1, 0, 1) */
 			}
-			if (e == e_hi) {
-				T *st = P.xstage[1] + rowidx;
+		}
+		if (e_hi >= 0 && P.xstage[1]) {
+			T *st = P.xstage[1] + rowidx;
+#pragma unroll
+			for (int e = 0; e < VEC; e++) if (e == e_hi) {
 				st[0] = v[0][e];                               /* ( 1, 0, 0) */
 				st[1 * P.xface_n + 1] = v[4][e];               /* ( 1, 1, 0) */
 				st[2 * P.xface_n - 1] = v[6][e];               /* ( 1,-1, 0) */
@@ -715,14 +802,14 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	}
 }
 
-template <typename T, int VEC, bool SMAG, bool STORE, int ORDER, bool XPUSH>
+template <typename T, int VEC, bool SMAG, bool STORE, int ORDER, bool XFUSE>
 __global__ void lbm_beta_general_kernel(const StepParams<T> P)
 {
 	long long gid, poff;
 	if (!box_cell<T, VEC>(P, gid, poff)) return;
 	if (!beta_block_is_general<T, VEC>(P)) return;
 	const long long DY = P.sx, DZ = P.sxy;
-	const int gx0 = XPUSH ? (int)((unsigned int)poff % (unsigned int)P.sx) : 0;
+	const int gx0 = XFUSE ? (int)((unsigned int)poff % (unsigned int)P.sx) : 0;
 #pragma unroll 1
 	for (int e = 0; e < VEC; e++) {
 		const long long c = gid + e;
@@ -753,27 +840,40 @@ __global__ void lbm_beta_general_kernel(const StepParams<T> P)
 #pragma unroll
 		for (int i = 0; i < 18; i++) d[i ^ 1] = P.dd[L[i]];
 		d[18] = P.dd[18LL * P.ns + c];
+		/* XFUSE works by LOCATION here (the wrap and the work-group quirk move cells around): whatever
+		 * this cell reads out of / writes into an x ghost column with a neighbour behind it comes from
+		 * my receive block / also goes to the neighbour's */
+		const bool xedge = XFUSE && (P.wg > 0 || gx0 + e <= 1 || gx0 + e >= P.sx - 2);
+		if (XFUSE && xedge) {
+#pragma unroll
+			for (int k = 0; k < 5; k++) {
+				const int jm = 2 * k + (k ? 3 : 1), jp = 2 * k + (k ? 2 : 0);      /* kXMinus[k], kXPlus[k] */
+				if (P.xpull[0]) {
+					const long long loc = L[jm] - (long long)jm * P.ns;
+					if (loc % P.sx == 0) d[jm ^ 1] = __ldcg(P.xpull[0] + k * P.xface_n + loc / P.sx);
+				}
+				if (P.xpull[1]) {
+					const long long loc = L[jp] - (long long)jp * P.ns;
+					if (loc % P.sx == P.sx - 1) d[jp ^ 1] = __ldcg(P.xpull[1] + k * P.xface_n + loc / P.sx);
+				}
+			}
+		}
 		T rho, vx, vy, vz;
 		beta_cell<T, SMAG, ORDER>(d, flag, P, rho, vx, vy, vz);
 #pragma unroll
 		for (int i = 0; i < 18; i++) P.dd[L[i]] = d[i];
 		P.dd[18LL * P.ns + c] = d[18];
-		if (XPUSH) {
-			/* by LOCATION (the wrap and the work-group quirk move cells around): whatever this cell
-			 * writes into an x ghost column with a neighbour behind it also goes to that neighbour */
-			const int x = gx0 + e;
-			if (P.wg > 0 || x <= 1 || x >= P.sx - 2) {
+		if (XFUSE && xedge) {
 #pragma unroll
-				for (int k = 0; k < 5; k++) {
-					const int jm = 2 * k + (k ? 3 : 1), jp = 2 * k + (k ? 2 : 0);      /* kXMinus[k], kXPlus[k] */
-					if (P.xstage[0]) {
-						const long long loc = L[jm] - (long long)jm * P.ns;
-						if (loc % P.sx == 0) P.xstage[0][k * P.xface_n + loc / P.sx] = d[jm];
-					}
-					if (P.xstage[1]) {
-						const long long loc = L[jp] - (long long)jp * P.ns;
-						if (loc % P.sx == P.sx - 1) P.xstage[1][k * P.xface_n + loc / P.sx] = d[jp];
-					}
+			for (int k = 0; k < 5; k++) {
+				const int jm = 2 * k + (k ? 3 : 1), jp = 2 * k + (k ? 2 : 0);
+				if (P.xstage[0]) {
+					const long long loc = L[jm] - (long long)jm * P.ns;
+					if (loc % P.sx == 0) P.xstage[0][k * P.xface_n + loc / P.sx] = d[jm];
+				}
+				if (P.xstage[1]) {
+					const long long loc = L[jp] - (long long)jp * P.ns;
+					if (loc % P.sx == P.sx - 1) P.xstage[1][k * P.xface_n + loc / P.sx] = d[jp];
 				}
 			}
 		}
@@ -857,7 +957,7 @@ __global__ void rect_copy_kernel(const T *__restrict__ src, T *__restrict__ dst,
  *                          them STRAIGHT INTO the neighbours' staging buffers (peer stores: pack +
  *                          send fused); the last block of a face publishes a sequence number in the
  *                          neighbour's flag word;
- *   XPUSH step kernels     the same for x faces from inside lbm_alpha/beta_kernel (the owning threads
+ *   XFUSE step kernels     the same for x faces from inside lbm_alpha/beta_kernel (the owning threads
  *                          hold the values in registers), completed by halo_xrim_flag_kernel;
  *   halo_wait_kernel       one thread per face waits (acquire, system scope) until the local flag
  *                          reaches the next sequence number;
@@ -955,13 +1055,39 @@ __global__ void halo_push_kernel(const HaloAxis A)
 	halo_publish(F);
 }
 
-/* x faces whose bulk went out of the step kernels (XPUSH): the rim pass.  The cells of an x face that lie
+/* wait until the neighbour's push has raised my flag to the next sequence number (acquire at system
+ * scope).  The expected number is counted in device memory.  A neighbour that never arrives (crashed
+ * rank) must not hang the GPU: after timeout_ns the wait gives up and leaves a mark the host finds
+ * in lbmWait. */
+__device__ __forceinline__ void halo_wait_face(const HaloFace &F, unsigned long long timeout_ns, unsigned int *error_word)
+{
+	const unsigned int seq = *F.sync_count + 1u;
+	*F.sync_count = seq;
+	unsigned long long t0 = 0;
+	unsigned int spins = 0;
+	/* sequence numbers only grow; signed distance tolerates wrap-around */
+	while ((int)(*F.flag - seq) < 0) {
+		__nanosleep(40);
+		if ((++spins & 1023u) == 0) {
+			unsigned long long now;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+			if (t0 == 0) t0 = now;
+			else if (now - t0 > timeout_ns) { atomicExch(error_word, 1u); break; }
+		}
+	}
+	__threadfence_system();
+}
+
+/* x faces whose bulk went out of the step kernels (XFUSE): the rim pass.  The cells of an x face that lie
  * in the two outermost layers of y or z hold values the y/z phases of THIS sync delivered (edge
  * populations on their way to the diagonal neighbour) or are ghost cells the step kernel skipped; they
  * are re-read from dd -- final by now: this kernel runs behind the step kernels and the y/z unpack -- and
- * stored over whatever the step kernel sent for them.  Then the flag goes up.  F.origin[0] = column. */
+ * stored over whatever the step kernel sent for them.  Then the flag goes up.  F.origin[0] = column.
+ * nwait > 0: one thread per face then waits for the neighbour's flag in the same launch (W = my receive
+ * side): the whole exposed x tail of a step is this one small kernel. */
 template <typename T>
-__global__ void halo_xrim_flag_kernel(const HaloAxis A)
+__global__ void halo_xrim_flag_kernel(const HaloAxis A, const HaloAxis W, int nwait,
+		unsigned long long timeout_ns, unsigned int *error_word)
 {
 	const HaloFace &F = A.f[blockIdx.y];
 	const int sy = F.size[1], sz = F.size[2];
@@ -986,31 +1112,13 @@ __global__ void halo_xrim_flag_kernel(const HaloAxis A)
 			dd[(long long)F.dd_comp[c] * F.dd_stride + F.origin[0] + (long long)y * F.ss[0] + (long long)z * F.ss[0] * F.ss[1]];
 	}
 	halo_publish(F);
+	if (blockIdx.x == 0 && (int)blockIdx.y < nwait && threadIdx.x == 64) halo_wait_face(W.f[blockIdx.y], timeout_ns, error_word);
 }
 
-/* wait: ONE thread per face (not a grid of spinning blocks next to the step kernel) waits until the
- * neighbour's push has raised my flag to the next sequence number (acquire at system scope).  The
- * expected number is counted in device memory.  A neighbour that never arrives (crashed rank) must
- * not hang the GPU: after timeout_ns the wait gives up and leaves a mark the host finds in lbmWait. */
+/* wait: ONE thread per face (not a grid of spinning blocks next to the step kernel) */
 __global__ void halo_wait_kernel(const HaloAxis A, int nfaces, unsigned long long timeout_ns, unsigned int *error_word)
 {
-	if ((int)threadIdx.x >= nfaces) return;
-	const HaloFace &F = A.f[threadIdx.x];
-	const unsigned int seq = *F.sync_count + 1u;
-	*F.sync_count = seq;
-	unsigned long long t0 = 0;
-	unsigned int spins = 0;
-	/* sequence numbers only grow; signed distance tolerates wrap-around */
-	while ((int)(*F.flag - seq) < 0) {
-		__nanosleep(40);
-		if ((++spins & 1023u) == 0) {
-			unsigned long long now;
-			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-			if (t0 == 0) t0 = now;
-			else if (now - t0 > timeout_ns) { atomicExch(error_word, 1u + threadIdx.x + 2u * blockIdx.x); break; }
-		}
-	}
-	__threadfence_system();
+	if ((int)threadIdx.x < nfaces) halo_wait_face(A.f[threadIdx.x], timeout_ns, error_word);
 }
 
 /* unpack: my receive block(s) of one axis -> the dd rects; runs behind halo_wait_kernel in stream
