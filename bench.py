@@ -277,6 +277,68 @@ def workload_config(args, n):
             "l2": "working set %.2f GB per GPU >> 126 MB L2 (no flush needed)" % ws}
 
 
+# ====================================================================== parity leg
+def verify_parity(args, rank, world, local, dist, backend, axis_order, np_dtype):
+    """A small run of the SAME decomposition, transport, phase order, precision, Smagorinsky constant and
+    kernel instantiations as the timed workload (sub-domains of 40 x 24 x 16 cells: rows no divisor of 128, so
+    the production kernels run), 12 steps, every population and flag of every rank compared bit for bit
+    with the CPU oracle's decomposed run (oracle/multi.py; the oracle is only the checker here).  The verdict
+    travels in the JSON line, so a multi-GPU scaling job carries its own parity evidence."""
+    import torch
+    from turbulent_lbm_multigpu_b200.configuration import CConfiguration
+    from turbulent_lbm_multigpu_b200.controller import CManager
+    from turbulent_lbm_multigpu_b200.domain import CDomain
+    steps, sub = 12, (40, 24, 16)
+    nums = decomposition(world, args.decomp)
+    D = tuple(s * k for s, k in zip(sub, nums))
+    L = (0.1, 0.1, 0.1)
+    cfg = CConfiguration()
+    cfg.domain_size, cfg.subdomain_num, cfg.smagorinsky_constant = D, nums, args.cs
+    cs_, ms_ = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
+    mgr = CManager(CDomain(-1, D, (0, 0, 0), L), nums, backend=backend, device=local, config=cfg,
+                   sync_mode=args.sync if world > 1 else "host", dtype=np_dtype, axis_order=axis_order,
+                   store_velocity=False, store_density=False,
+                   compute_stream=cs_.cuda_stream, comm_stream=ms_.cuda_stream)
+    mgr.initSimulation(rank)
+    ctrl = mgr.getController()
+    for _ in range(steps):
+        ctrl.computeNextStep()
+    s = ctrl.getSolver()
+    s.wait()
+    mine = (s.storeDensityDistribution(), s.storeFlags(), s.config())
+    s.close()
+    gathered = [mine]
+    if dist is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+    if rank != 0:
+        return None
+    out = {"ok": False, "steps": steps, "subdomain_size": list(sub), "subdomain_num": list(nums), "ranks": world,
+           "compared": "19 populations + flags of every cell (ghost layers included) of every rank, bit-exact, "
+                       "against the CPU oracle's decomposed run (oracle/multi.py)"}
+    try:
+        from oracle import multi as omulti
+        make, _ = omulti.make_oracle_factory(D, nums, L, dtype=np_dtype, variant=0, smagorinsky_cs=args.cs)
+        md = omulti.MultiDomain(D, nums, make, slots="reference" if (world > 1 and args.sync == "host") else "minimal",
+                                axis_order=(2, 1, 0) if axis_order == "zyx" else (0, 1, 2))
+        md.run(steps)
+        bad = []
+        for r in range(world):
+            dd, fl, kc = gathered[r]
+            o = md.ranks[r]["solver"]
+            if not (np.array_equal(dd.view(np.uint8), o.dd.view(np.uint8)) and np.array_equal(fl, o.flags)):
+                bad.append(r)
+            if kc["wg_quirk"] != 0:
+                bad.append(("quirk", r))
+        out["ok"] = not bad
+        if bad:
+            out["differing_ranks"] = bad
+    except Exception as e:         # the checker being absent is reported, not hidden
+        out["ok"] = None
+        out["error"] = "oracle unavailable: %s" % e
+    return out
+
+
 # ====================================================================== GPU arm
 def run_gpu(args):
     import torch
@@ -333,9 +395,24 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    parity = None
+    if not args.no_verify:
+        parity = verify_parity(args, rank, world, local, dist, backend, axis_order, np_dtype)
+        barrier()
+
     W, K = max(3, args.warmup), args.steps
     W += W & 1                              # whole beta/alpha cycles
     K += K & 1
+    if args.min_seconds > 0:                # sustained run: enough steps for the requested wall time
+        for _ in range(4):
+            ctrl.computeNextStep()
+        barrier()
+        s.timerStart()
+        for _ in range(10):
+            ctrl.computeNextStep()
+        est = max_over_ranks(s.timerStop()) / 10.0
+        K = max(K, int(args.min_seconds * 1e3 / max(est, 1e-3)) + 1)
+        K += K & 1
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                     # sampled from the warm-up on: the timed region is short
@@ -448,7 +525,10 @@ def run_gpu(args):
     dt = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": cells_global * K / dt / 1e6, "unit": "MLUPS",
            "h2d_bytes_per_step": int(lid_np.nbytes) * n, "d2h_bytes_per_step": int(probe_np.nbytes) * n,
-           "api": "CLbmSolver.setFlags + CController.computeNextStep + storeDensityDistribution (pinned host buffers)"}
+           "api": "CLbmSolver.setFlags + CController.computeNextStep + storeDensityDistribution (pinned host buffers)",
+           "note": "the step's host input is one boundary plane of flags, its host output one line of populations: the "
+                   "copies are small by nature of the workload (the lattice stays resident in HBM); e2e < value is "
+                   "the per-step host round trip (two blocking copies), not bandwidth"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -473,6 +553,7 @@ def run_gpu(args):
                          "note": "per GPU; step kernels lbm_alpha_kernel/lbm_beta_kernel alternate; %d B per "
                                  "lattice-site update x cells per launch / CUDA-event time" % bytes_per_lup},
             "halo": halo,
+            "parity": parity,
             "sync_mode": args.sync if world > 1 else None, "axis_order": axis_order if world > 1 else None,
             "cuda_graph": graph is not None,
             "kernel_config": s.config(),

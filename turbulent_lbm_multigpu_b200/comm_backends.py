@@ -3,9 +3,9 @@ CController::syncAlpha/syncBeta (reference src/CController.hpp:299-311,361-373).
 
 * ``TorchDistributedBackend``: one process per sub-domain/GPU (torchrun); NCCL send/recv
   on device buffers over NVLink, or gloo on host buffers (CPU tests, host-staged mode).
-* ``InProcessBackend``: all sub-domains live in one process (single-process multi-device
-  or several sub-domains on one device); payloads are handed over directly, or moved by
-  one peer-copy kernel (``haloCopyPeer``) without any staging.
+
+Sub-domains that share a process need no backend at all: ``controller.InProcessSimulation`` moves
+their halos with the library's peer-copy / push-pull kernels directly.
 """
 from __future__ import annotations
 
@@ -35,16 +35,3 @@ class TorchDistributedBackend:
 
     def barrier(self):
         self.dist.barrier(self.group)
-
-
-class InProcessBackend:
-    """Mailbox between controllers that share a process."""
-
-    def __init__(self):
-        self.controllers = {}
-
-    def register(self, rank, controller):
-        self.controllers[rank] = controller
-
-    def peer(self, rank):
-        return self.controllers[rank]

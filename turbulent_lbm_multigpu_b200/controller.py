@@ -278,6 +278,23 @@ class CController:
                 self.vector_checksum = s.getVelocityChecksum()
                 print("Checksum: %.8f" % (float(self.vector_checksum) * 1000.0))
             print("done.")
+        # BENCHMARK block of src/CController.hpp:445-477: rank 0 appends the max-over-ranks time and the
+        # whole-domain rates to ./output/benchmark/benchmark_<np>.ini (compile-time switch in the reference,
+        # LBM_B200_BENCHMARK in the environment here, like the C++ host)
+        import os
+        if os.environ.get("LBM_B200_BENCHMARK"):
+            gtime = seconds
+            if self.backend is not None and getattr(self.backend, "world", 1) > 1:
+                gtime = self.backend.max_over_ranks(seconds)
+            if self._UID <= 0:
+                nproc = int(np.prod(cfg.subdomain_num))
+                gfps = loops / gtime if gtime > 0 else float("inf")
+                gmlups = gfps * float(np.prod(cfg.domain_size)) * 1e-6
+                os.makedirs(os.path.join("output", "benchmark"), exist_ok=True)
+                with open(os.path.join("output", "benchmark", "benchmark_%d.ini" % nproc), "a") as f:
+                    f.write("CUBE_X : %d\nCUBE_Y : %d\nCUBE_Z : %d\n" % tuple(cfg.domain_size))
+                    f.write("SECONDS : %g\nFPS : %g\nMLUPS : %g\nBANDWIDTH : %g\n\n"
+                            % (gtime, gfps, gmlups, gmlups * floats_per_cell * self.dtype.itemsize))
         # PROFILE block of src/CController.hpp:503-519 (run-time switch: LBM_B200_PROFILE, or
         # CLbmSolver.profileEnable before run)
         count = getattr(s, "profileEventCount", None)   # an injected solver need not carry the timeline

@@ -485,12 +485,13 @@ __device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
 	return box_cell<T, VEC>(P, gid, off);
 }
 
-/* XFUSE: which element of this thread's VEC-wide group is the cell next to the low / high x ghost
- * face (-1: none), and the cell's index in the face [z][y].  off = offset of the group inside its plane.
- * Cheap (block-uniform division) when rows are whole multiples of a block; re-evaluated at each use
- * instead of being kept in registers across the collision (the volatile read of %ctaid defeats CSE). */
+/* XFUSE: is one cell of this thread's VEC-wide group the cell next to the low (side 0) / high (side 1)
+ * x ghost face?  Returns the side (-1: no), the element and the cell's index in the face [z][y].
+ * (sx >= 2 * VEC + 2 is required, so a thread never holds both.)  off = offset of the group inside its
+ * plane.  Cheap (block-uniform division) when rows are whole multiples of a block; re-evaluated at each
+ * use instead of being kept in registers across the collision (the volatile read of %ctaid defeats CSE). */
 template <typename T, int VEC>
-__device__ __forceinline__ void xfuse_lanes(const StepParams<T> &P, long long off, int &e_lo, int &e_hi, long long &rowidx)
+__device__ __forceinline__ int xfuse_lane(const StepParams<T> &P, long long off, int &e, long long &rowidx)
 {
 	unsigned int y;
 	int x0;
@@ -506,8 +507,10 @@ __device__ __forceinline__ void xfuse_lanes(const StepParams<T> &P, long long of
 		x0 = (int)(po - y * (unsigned int)P.sx);
 	}
 	rowidx = (long long)box_z(P) * P.sy + y;
-	e_lo = (x0 <= 1 && 1 < x0 + VEC) ? 1 - x0 : -1;
-	e_hi = (x0 <= P.sx - 2 && P.sx - 2 < x0 + VEC) ? P.sx - 2 - x0 : -1;
+	if (x0 <= 1 && 1 < x0 + VEC) { e = 1 - x0; return 0; }
+	if (x0 <= P.sx - 2 && P.sx - 2 < x0 + VEC) { e = P.sx - 2 - x0; return 1; }
+	e = -1;
+	return -1;
 }
 
 /* ================================================================== ALPHA kernel */
@@ -525,46 +528,43 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 	bool all_ghost = true;
 #pragma unroll
 	for (int e = 0; e < VEC; e++) all_ghost &= (flag[e] == FLAG_GHOST);
-	/* lbm_alpha.cl:31-32: ghost cells are skipped; obstacle cells write nothing (:305-343).  A group
-	 * that holds the cell next to an x face still pulls / ships that cell's slots. */
-	bool xlane = false;
-	if (XFUSE && (all_ghost || (!any_write && !STORE))) {
-		int e_lo, e_hi;
+	/* XFUSE PULL, issued first so that it overlaps the 19 slot loads: what the x neighbour's beta step
+	 * streamed into the cell next to the face sits in my receive block (the reference's
+	 * setDensityDistribution(..., norm) would have scattered it into these slots) */
+	T px[5] = { 0, 0, 0, 0, 0 };
+	int pside = -1, pe = -1;
+	if (XFUSE) {
 		long long rowidx;
-		xfuse_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
-		xlane = (e_lo >= 0 && (P.xpull[0] || P.xstage[0])) || (e_hi >= 0 && (P.xpull[1] || P.xstage[1]));
+		const int side = xfuse_lane<T, VEC>(P, poff, pe, rowidx);
+		if (side >= 0 && P.xpull[side]) {
+			const T *st = P.xpull[side] + rowidx;
+			pside = side;
+#pragma unroll
+			for (int k = 0; k < 5; k++) px[k] = __ldcg(st + k * P.xface_n);
+		}
+		/* lbm_alpha.cl:31-32: ghost cells are skipped; obstacle cells write nothing (:305-343).  A group
+		 * that holds the cell next to an x face still pulls / ships that cell's slots. */
+		const bool xlane = side >= 0 && (P.xpull[side] || P.xstage[side]);
+		if (all_ghost && !xlane) return;
+		if (!any_write && !STORE && !xlane) return;
+	} else {
+		if (all_ghost) return;
+		if (!any_write && !STORE) return;
 	}
-	if (all_ghost && !xlane) return;
-	if (!any_write && !STORE && !xlane) return;
 
 	T v[19][VEC];
 	T *base = P.dd + gid;
 #pragma unroll
 	for (int i = 0; i < 19; i++) VecIO<T, VEC>::load(base + (long long)i * P.ns, v[i]);
 
-	bool pulled = false;
-	if (XFUSE) {
-		/* PULL: what the x neighbour's beta step streamed into this cell sits in my receive block
-		 * (the reference's setDensityDistribution(..., norm) would have scattered it into these slots) */
-		int e_lo, e_hi;
-		long long rowidx;
-		xfuse_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
-		if (e_lo >= 0 && P.xpull[0]) {
-			const T *st = P.xpull[0] + rowidx;
-			pulled = true;
+	const bool pulled = XFUSE && pside >= 0;
+	if (XFUSE && pside >= 0) {
 #pragma unroll
-			for (int e = 0; e < VEC; e++) if (e == e_lo) {
+		for (int e = 0; e < VEC; e++) if (e == pe) {
 #pragma unroll
-				for (int k = 0; k < 5; k++) v[2 * k + (k ? 2 : 0)][e] = __ldcg(st + k * P.xface_n);     /* slots 0,4,6,8,10 */
-			}
-		}
-		if (e_hi >= 0 && P.xpull[1]) {
-			const T *st = P.xpull[1] + rowidx;
-			pulled = true;
-#pragma unroll
-			for (int e = 0; e < VEC; e++) if (e == e_hi) {
-#pragma unroll
-				for (int k = 0; k < 5; k++) v[2 * k + (k ? 3 : 1)][e] = __ldcg(st + k * P.xface_n);     /* slots 1,5,7,9,11 */
+			for (int k = 0; k < 5; k++) {
+				if (pside == 0) v[2 * k + (k ? 2 : 0)][e] = px[k];     /* low face: slots 0,4,6,8,10 */
+				else v[2 * k + (k ? 3 : 1)][e] = px[k];                /* high face: slots 1,5,7,9,11 */
 			}
 		}
 	}
@@ -595,23 +595,17 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 	if (XFUSE) {
 		/* PUSH: slot j holds v[j^1] after this step.  Ghost cells (rims of the y/z faces) are left to
 		 * the rim pass that follows the y/z unpack (halo_xrim_flag_kernel). */
-		int e_lo, e_hi;
+		int e1;
 		long long rowidx;
-		xfuse_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
-		if (e_lo >= 0 && P.xstage[0]) {
-			T *st = P.xstage[0] + rowidx;
+		const int side = xfuse_lane<T, VEC>(P, poff, e1, rowidx);
+		if (side >= 0 && P.xstage[side]) {
+			T *st = P.xstage[side] + rowidx;
 #pragma unroll
-			for (int e = 0; e < VEC; e++) if (e == e_lo && flag[e] != FLAG_GHOST) {
+			for (int e = 0; e < VEC; e++) if (e == e1 && flag[e] != FLAG_GHOST) {
 #pragma unroll
-				for (int k = 0; k < 5; k++) st[k * P.xface_n] = v[2 * k + (k ? 3 : 1)][e];   /* slots 0,4,6,8,10 <- v[1,5,7,9,11] */
-			}
-		}
-		if (e_hi >= 0 && P.xstage[1]) {
-			T *st = P.xstage[1] + rowidx;
-#pragma unroll
-			for (int e = 0; e < VEC; e++) if (e == e_hi && flag[e] != FLAG_GHOST) {
-#pragma unroll
-				for (int k = 0; k < 5; k++) st[k * P.xface_n] = v[2 * k + (k ? 2 : 0)][e];   /* slots 1,5,7,9,11 <- v[0,4,6,8,10] */
+				for (int k = 0; k < 5; k++)
+					st[k * P.xface_n] = side == 0 ? v[2 * k + (k ? 3 : 1)][e]      /* slots 0,4,6,8,10 <- v[1,5,7,9,11] */
+					                              : v[2 * k + (k ? 2 : 0)][e];     /* slots 1,5,7,9,11 <- v[0,4,6,8,10] */
 			}
 		}
 	}
@@ -676,6 +670,26 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	if (beta_block_is_general<T, VEC>(P)) return;
 
 	const long long DY = P.sx, DZ = P.sxy;
+	/* XFUSE PULL, issued first so that it overlaps the slot loads: location (slot j, c + e_j) in the ghost
+	 * column next to the x = 1 (x = sx-2) cell holds what the neighbour's alpha step left there -- it sits
+	 * in my receive block at face index row(c) + e_y + e_z * sy (in range: this path is a plane + a row
+	 * away from the array ends); it is read as d[j^1]. */
+	T px[5] = { 0, 0, 0, 0, 0 };
+	int pside = -1, pe = -1;
+	if (XFUSE) {
+		long long rowidx;
+		const int side = xfuse_lane<T, VEC>(P, poff, pe, rowidx);
+		if (side >= 0 && P.xpull[side]) {
+			const T *st = P.xpull[side] + rowidx;
+			const long long sgn = side == 0 ? 1 : -1;          /* e_y, e_z of the high face's slots are mirrored */
+			pside = side;
+			px[0] = __ldcg(st);                                     /* slot 1 (-1, 0, 0) | slot 0 ( 1, 0, 0) */
+			px[1] = __ldcg(st + 1 * P.xface_n - sgn);               /* slot 5 (-1,-1, 0) | slot 4 ( 1, 1, 0) */
+			px[2] = __ldcg(st + 2 * P.xface_n + sgn);               /* slot 7 (-1, 1, 0) | slot 6 ( 1,-1, 0) */
+			px[3] = __ldcg(st + 3 * P.xface_n - sgn * P.sy);        /* slot 9 (-1, 0,-1) | slot 8 ( 1, 0, 1) */
+			px[4] = __ldcg(st + 4 * P.xface_n + sgn * P.sy);        /* slot 11 (-1, 0, 1) | slot 10 ( 1, 0,-1) */
+		}
+	}
 	int flag[VEC];
 	FlagIO<VEC>::load(P.flags + gid, flag);
 
@@ -708,34 +722,13 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	}
 	VecIO<T, VEC>::load(base + 18LL * P.ns, v[18]);
 
-	if (XFUSE) {
-		/* PULL: location (slot j, c + e_j) in the ghost column next to the x = 1 (x = sx-2) cell holds
-		 * what the neighbour's alpha step left there -- it sits in my receive block at face index
-		 * row(c) + e_y + e_z * sy (in range: this path is a plane + a row away from the array ends);
-		 * it is read as d[j^1]. */
-		int e_lo, e_hi;
-		long long rowidx;
-		xfuse_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
-		if (e_lo >= 0 && P.xpull[0]) {
-			const T *st = P.xpull[0] + rowidx;
+	if (XFUSE && pside >= 0) {
 #pragma unroll
-			for (int e = 0; e < VEC; e++) if (e == e_lo) {
-				v[0][e] = __ldcg(st);                              /* slot 1  (-1, 0, 0) */
-				v[4][e] = __ldcg(st + 1 * P.xface_n - 1);          /* slot 5  (-1,-1, 0) */
-				v[6][e] = __ldcg(st + 2 * P.xface_n + 1);          /* slot 7  (-1, 1, 0) */
-				v[8][e] = __ldcg(st + 3 * P.xface_n - P.sy);       /* slot 9  (-1, 0,-1) */
-				v[10][e] = __ldcg(st + 4 * P.xface_n + P.sy);      /* slot 11 (-1, 0, 1) */
-			}
-		}
-		if (e_hi >= 0 && P.xpull[1]) {
-			const T *st = P.xpull[1] + rowidx;
+		for (int e = 0; e < VEC; e++) if (e == pe) {
 #pragma unroll
-			for (int e = 0; e < VEC; e++) if (e == e_hi) {
-				v[1][e] = __ldcg(st);                              /* slot 0  ( 1, 0, 0) */
-				v[5][e] = __ldcg(st + 1 * P.xface_n + 1);          /* slot 4  ( 1, 1, 0) */
-				v[7][e] = __ldcg(st + 2 * P.xface_n - 1);          /* slot 6  ( 1,-1, 0) */
-				v[9][e] = __ldcg(st + 3 * P.xface_n + P.sy);       /* slot 8  ( 1, 0, 1) */
-				v[11][e] = __ldcg(st + 4 * P.xface_n - P.sy);      /* slot 10 ( 1, 0,-1) */
+			for (int k = 0; k < 5; k++) {
+				if (pside == 0) v[2 * k + (k ? 2 : 0)][e] = px[k];     /* read as d[j^1], j = 1,5,7,9,11 */
+				else v[2 * k + (k ? 3 : 1)][e] = px[k];                /* j = 0,4,6,8,10 */
 			}
 		}
 	}
@@ -761,29 +754,19 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	if (XFUSE) {
 		/* PUSH: the x = 1 (x = sx-2) cell is the only writer of the e_x = -1 (+1) slots of the ghost
 		 * column next to it; the same values go to the neighbour, same face index as above. */
-		int e_lo, e_hi;
+		int e1;
 		long long rowidx;
-		xfuse_lanes<T, VEC>(P, poff, e_lo, e_hi, rowidx);
-		if (e_lo >= 0 && P.xstage[0]) {
-			T *st = P.xstage[0] + rowidx;
+		const int side = xfuse_lane<T, VEC>(P, poff, e1, rowidx);
+		if (side >= 0 && P.xstage[side]) {
+			T *st = P.xstage[side] + rowidx;
+			const long long sgn = side == 0 ? 1 : -1;
 #pragma unroll
-			for (int e = 0; e < VEC; e++) if (e == e_lo) {
-				st[0] = v[1][e];                               /* (-1, 0, 0) */
-				st[1 * P.xface_n - 1] = v[5][e];               /* (-1,-1, 0) */
-				st[2 * P.xface_n + 1] = v[7][e];               /* (-1, 1, 0) */
-				st[3 * P.xface_n - P.sy] = v[9][e];            /* (-1, 0,-1) */
-				st[4 * P.xface_n + P.sy] = v[11][e];           /* (-1, 0, 1) */
-			}
-		}
-		if (e_hi >= 0 && P.xstage[1]) {
-			T *st = P.xstage[1] + rowidx;
-#pragma unroll
-			for (int e = 0; e < VEC; e++) if (e == e_hi) {
-				st[0] = v[0][e];                               /* ( 1, 0, 0) */
-				st[1 * P.xface_n + 1] = v[4][e];               /* ( 1, 1, 0) */
-				st[2 * P.xface_n - 1] = v[6][e];               /* ( 1,-1, 0) */
-				st[3 * P.xface_n + P.sy] = v[8][e];            /* ( 1, 0, 1) */
-				st[4 * P.xface_n - P.sy] = v[10][e];           /* ( 1, 0,-1) */
+			for (int e = 0; e < VEC; e++) if (e == e1) {
+				st[0] = side == 0 ? v[1][e] : v[0][e];
+				st[1 * P.xface_n - sgn] = side == 0 ? v[5][e] : v[4][e];
+				st[2 * P.xface_n + sgn] = side == 0 ? v[7][e] : v[6][e];
+				st[3 * P.xface_n - sgn * P.sy] = side == 0 ? v[9][e] : v[8][e];
+				st[4 * P.xface_n + sgn * P.sy] = side == 0 ? v[11][e] : v[10][e];
 			}
 		}
 	}

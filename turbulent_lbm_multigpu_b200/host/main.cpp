@@ -18,6 +18,7 @@
 #include <iostream>
 #include <string>
 #include <thread>
+#include <exception>
 #include <vector>
 
 #include "CManager.hpp"
@@ -80,6 +81,16 @@ static void rank_main(int rank, CDomain<T> domain, CVector<3, int> nums, CRankWo
 		world->barrier();           /* nobody unmaps halo blocks while a neighbour may still write */
 	} catch (const char *msg) {
 		std::cerr << "rank " << rank << ": " << msg << std::endl;
+		world->fail();
+		*status = 1;
+	} catch (const std::exception &e) {
+		/* bad_alloc from the validation / recv buffers, system_error ...: release the peers from their
+		 * barriers and device-side flag waits instead of std::terminate */
+		std::cerr << "rank " << rank << ": " << e.what() << std::endl;
+		world->fail();
+		*status = 1;
+	} catch (...) {
+		std::cerr << "rank " << rank << ": unknown exception" << std::endl;
 		world->fail();
 		*status = 1;
 	}
