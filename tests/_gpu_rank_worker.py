@@ -50,7 +50,7 @@ def main():
     compute_stream, comm_stream = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
     mgr = CManager(CDomain(-1, D, (0, 0, 0), (0.1, 0.1, 0.1)), nums, backend=TorchDistributedBackend(),
                    device=local, sync_mode=sync, config=cfg, dtype=dtype,
-                   beta_order=order, axis_order=axis_order,
+                   beta_order=order, axis_order=axis_order, block_size=int(os.environ.get("LBM_TEST_BLOCK") or 0),
                    compute_stream=compute_stream.cuda_stream, comm_stream=comm_stream.cuda_stream)
     mgr.initSimulation(rank)
     ctrl = mgr.getController()

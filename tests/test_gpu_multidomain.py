@@ -156,7 +156,36 @@ def test_bench_defaults_decomposed_equal_oracle(D, nums, steps, dtype, cs):
         assert bits_equal(s.storeVelocity(origin=(1, 1, 1), size=inner), single.storeVelocity(origin=o, size=inner)), (r, "velocity")
 
 
-@pytest.mark.parametrize("D,nums", [((80, 24, 16), (2, 1, 1)), ((48, 40, 24), (2, 2, 2))])
+@pytest.mark.parametrize("D,nums,steps", [
+    ((384, 24, 16), (2, 1, 1), 21),      # rows of 192 cells = three 32-thread blocks, no work-group quirk: vectorised kernels
+    ((576, 24, 16), (3, 1, 1), 21),      # a rank with two x faces
+    ((384, 40, 24), (2, 2, 2), 31),      # blocks: rim lines forwarded from the y/z phases
+    ((128, 24, 16), (2, 1, 1), 31),      # rows of 64 cells = ONE block (both lanes in every block); 128 % 64 == 0, so the
+    ((128, 40, 24), (2, 2, 2), 41),      # work-group quirk is live and the scalar kernel does the exchange by location
+    ((256, 40, 12), (2, 2, 1), 40),      # rows of 128 cells, quirk live
+])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fused_x_exchange_with_small_blocks(D, nums, steps, dtype):
+    """The fused x exchange (step kernels push and pull the x faces themselves) needs rows that are whole
+    thread blocks; with 32-thread blocks that is 64 cells, small enough for the oracle."""
+    L = (0.1, 0.1, 0.1)
+    cfg = _cfg()
+    cfg.smagorinsky_constant = 0.1
+    sim = InProcessSimulation(CDomain(-1, D, (0, 0, 0), L), nums, transport="p2p", overlap=True, config=cfg,
+                              dtype=dtype, axis_order="zyx", block_size=32)
+    for c in sim.controllers:
+        k = c.getSolver().config()
+        assert k["vector_width"] == 2 and k["block_size"] == 32
+        assert (k["wg_quirk"] == 0) == (128 % sim.sub_size[0] != 0)
+    sim.run(steps)
+    make, po = omulti.make_oracle_factory(D, nums, L, dtype=dtype, variant=0, smagorinsky_cs=0.1)
+    md = omulti.MultiDomain(D, nums, make, slots="minimal", axis_order=(2, 1, 0))
+    md.run(steps)
+    for r, ctrl in enumerate(sim.controllers):
+        assert bits_equal(ctrl.getSolver().storeDensityDistribution(), md.ranks[r]["solver"].dd), (r, "dd vs oracle")
+
+
+@pytest.mark.parametrize("D,nums", [((384, 24, 16), (2, 1, 1)), ((384, 40, 24), (2, 2, 2)), ((128, 24, 16), (2, 1, 1))])
 def test_fused_x_exchange_materialises_on_host_access(D, nums):
     """With the z,y,x order the x faces are received into their blocks and read from there by the next
     step kernel; a host read of the populations in between (any step parity) must still see them in dd, and
@@ -165,7 +194,7 @@ def test_fused_x_exchange_materialises_on_host_access(D, nums):
     cfg = _cfg()
     cfg.smagorinsky_constant = 0.1
     sim = InProcessSimulation(CDomain(-1, D, (0, 0, 0), L), nums, transport="p2p", overlap=True, config=cfg,
-                              dtype=np.float32, axis_order="zyx")
+                              dtype=np.float32, axis_order="zyx", block_size=32)
     make, po = omulti.make_oracle_factory(D, nums, L, dtype=np.float32, variant=0, smagorinsky_cs=0.1)
     md = omulti.MultiDomain(D, nums, make, slots="minimal", axis_order=(2, 1, 0))
     for chunk in (7, 1, 2, 5):

@@ -35,13 +35,14 @@ def _free_port():
 
 
 def _run_ranks(tmp_path, D, nums, steps, sync, axis_order="", order="linear", cs=0.0, dtype="f32", share=False,
-               graph=False):
+               graph=False, block=0):
     world = nums[0] * nums[1] * nums[2]
     if _gpus() < world and not share:
         pytest.skip("needs %d GPUs" % world)
     env = dict(os.environ, LBM_TEST_DOMAIN=",".join(map(str, D)), LBM_TEST_NUMS=",".join(map(str, nums)),
                LBM_TEST_STEPS=str(steps), LBM_TEST_SYNC=sync, LBM_TEST_OUT=str(tmp_path),
-               LBM_TEST_AXIS_ORDER=axis_order, LBM_TEST_BETA_ORDER=order, LBM_TEST_CS=repr(cs), LBM_TEST_DTYPE=dtype, LBM_TEST_GRAPH="1" if graph else "0")
+               LBM_TEST_AXIS_ORDER=axis_order, LBM_TEST_BETA_ORDER=order, LBM_TEST_CS=repr(cs), LBM_TEST_DTYPE=dtype, LBM_TEST_GRAPH="1" if graph else "0",
+               LBM_TEST_BLOCK=str(block))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(HERE, "_gpu_rank_worker.py")]
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
@@ -71,23 +72,26 @@ def test_eight_ranks_bench_defaults_equal_oracle(tmp_path, D, nums, steps, axis_
 
 @pytest.mark.parametrize("D,nums,steps,sync,axis_order", [
     ((40, 24, 32), (1, 1, 2), 11, "p2p", ""),
-    ((80, 24, 16), (2, 1, 1), 10, "p2p", "zyx"),
+    ((80, 24, 16), (2, 1, 1), 10, "p2p", "zyx"),          # rows no multiple of a block: separate x push / pull kernels
+    ((384, 24, 16), (2, 1, 1), 11, "p2p", "zyx:32"),      # fused x exchange (rows of 192 cells, 32-thread blocks)
     ((40, 24, 32), (1, 1, 2), 6, "host", ""),
 ])
 def test_two_processes_sharing_one_gpu(tmp_path, D, nums, steps, sync, axis_order):
     """The multi-process path (CUDA IPC mapped receive blocks, device-side flags) on whatever the box
     has -- two processes time-slice one GPU when there is only one.  Bench defaults otherwise."""
-    _run_ranks(tmp_path, D, nums, steps, sync, axis_order, order="shipped", cs=0.1, share=True)
+    axis_order, _, block = axis_order.partition(":")
+    _run_ranks(tmp_path, D, nums, steps, sync, axis_order, order="shipped", cs=0.1, share=True, block=int(block or 0))
 
 
 @pytest.mark.parametrize("D,nums,steps,axis_order", [
     ((40, 24, 32), (1, 1, 2), 104, ""),          # 51 replays of the captured beta+alpha cycle, z-slabs
-    ((80, 24, 16), (2, 1, 1), 104, "zyx"),       # x faces pushed from inside the step kernels
+    ((384, 24, 16), (2, 1, 1), 104, "zyx"),      # x faces exchanged from inside the step kernels (32-thread blocks)
 ])
 def test_cuda_graph_replay_keeps_synchronising(tmp_path, D, nums, steps, axis_order):
     """`bench.py --graph` with the p2p transport: the captured 2-step cycle replayed 51 times must equal the
     oracle's decomposed run -- the halo sequence numbers are counted on the device, not frozen in the graph."""
-    _run_ranks(tmp_path, D, nums, steps, "p2p", axis_order, order="shipped", cs=0.1, share=True, graph=True)
+    _run_ranks(tmp_path, D, nums, steps, "p2p", axis_order, order="shipped", cs=0.1, share=True, graph=True,
+               block=32 if axis_order == "zyx" else 0)
 
 
 @pytest.mark.parametrize("D,nums,steps,sync", [

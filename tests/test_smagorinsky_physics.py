@@ -21,9 +21,12 @@ W = np.array([np.float32(1.0) / np.float32(18.0)] * 4 + [np.float32(1.0) / np.fl
              + [np.float32(1.0) / np.float32(18.0)] * 2 + [np.float32(1.0) / np.float32(3.0)], dtype=np.float64)
 
 
-class _P:          # what helpers.make_* read from a parametrisation
-    def __init__(self, tau, u_lid, g=(0.0, 0.0, 0.0)):
-        self.tau, self.inv_tau, self.u_lid, self.gravitation = tau, 1.0 / tau, u_lid, g
+def _P(tau, u_lid, g=(0.0, 0.0, 0.0)):
+    """a parametrisation with a chosen relaxation time and lid speed (lattice units), no body force"""
+    from turbulent_lbm_multigpu_b200.skeleton import LbmParameters
+    return LbmParameters(dtype=np.float64, domain_cells=(0, 0, 0), d_cell_length=1.0, d_timestep=1.0, tau=tau,
+                         inv_tau=1.0 / tau, inv_trt_tau=1.0 / tau, gravitation=g,
+                         drivenCavityVelocity=(u_lid, 0.0, 0.0, 1.0), d_reynolds=0.0)
 
 
 def _model_tau_eff(d, tau, cs):

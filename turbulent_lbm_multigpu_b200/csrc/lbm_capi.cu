@@ -149,6 +149,8 @@ int flush_x_pending(lbm_t h, cudaStream_t s);
 bool x_fusable(lbm_t h)
 {
 	if (!h->xfuse || h->axis_order != LBM_AXIS_ORDER_ZYX) return false;
+	/* whole blocks per row (fixed lanes), one lane per thread, 32-bit face offsets */
+	if (h->sx % (h->block * h->vec) != 0 || h->sx < 2 * h->vec + 2 || 5LL * h->sy * h->sz >= 0x7fffffffLL) return false;
 	bool any = false;
 	for (size_t i = 0; i < h->faces.size(); i++) {
 		const lbm_face &f = h->faces[i];
@@ -168,6 +170,7 @@ StepParams<T> make_params(lbm_t h, const Box &b, bool alpha, bool xfuse)
 	P.xface_n = (long long)h->sy * h->sz;
 	const int cells_per_block = h->block * h->vec;
 	P.bpr = (b.nx == h->sx && b.x0 == 0 && h->sx % cells_per_block == 0) ? h->sx / cells_per_block : 0;
+	if (P.bpr == 0) xfuse = false;           /* (the boxes of an XFUSE step are whole rows; belt and braces) */
 	if (xfuse) {
 		const int kind = alpha ? LBM_SYNC_ALPHA : LBM_SYNC_BETA;          /* the sync this step feeds */
 		const int consumed = alpha ? LBM_SYNC_BETA : LBM_SYNC_ALPHA;      /* the sync this step consumes */
@@ -178,6 +181,10 @@ StepParams<T> make_params(lbm_t h, const Box &b, bool alpha, bool xfuse)
 			P.xstage[side] = (T *)(f.peer_block + f.peer_stage_off[kind]);
 			if (h->x_pending == 1 + consumed) P.xpull[side] = (const T *)(f.local_block + f.stage_off[consumed]);
 		}
+		/* timing experiments only (results are wrong without the exchange): LBM_B200_XFUSE_DEBUG=nopush|nopull|none */
+		static const char *dbg = getenv("LBM_B200_XFUSE_DEBUG");
+		if (dbg && (!strcmp(dbg, "nopush") || !strcmp(dbg, "none"))) P.xstage[0] = P.xstage[1] = NULL;
+		if (dbg && (!strcmp(dbg, "nopull") || !strcmp(dbg, "none"))) P.xpull[0] = P.xpull[1] = NULL;
 	}
 	P.dd = (T *)h->dd; P.flags = h->flags; P.velocity = (T *)h->velocity; P.density = (T *)h->density;
 	P.n = h->n; P.ns = h->stride; P.sx = h->sx; P.sy = h->sy; P.sz = h->sz; P.sxy = (long long)h->sx * h->sy;
@@ -1066,18 +1073,6 @@ int build_pull(lbm_t h, int kind, int axis, HaloAxis &A, unsigned &nf, unsigned 
 	return LBM_OK;
 }
 
-unsigned rim_blocks(const HaloAxis &A, unsigned nf)
-{
-	unsigned blocks = 1;
-	for (unsigned i = 0; i < nf; i++) {
-		const long long work = 4LL * (A.f[i].size[1] + A.f[i].size[2]) * A.f[i].ncomp;
-		unsigned b = (unsigned)((work + 255) / 256);
-		if (b > 148) b = 148;
-		if (b > blocks) blocks = b;
-	}
-	return blocks;
-}
-
 int axis_unpack(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed)
 {
 	HaloAxis A; unsigned nf, blocks;
@@ -1118,10 +1113,13 @@ int axis_push(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed, bool ri
 		HaloAxis W; unsigned nw = 0, wb;
 		if (with_wait) { if (int rc = build_pull(h, kind, axis, W, nw, wb, exposed)) return rc; }
 		else memset(&W, 0, sizeof(W));
-		dim3 grid(rim_blocks(A, nf), nf);
+		/* rim lines only exist where a y or z face has a neighbour (forwarded edges, ghost rims) */
+		int do_rim = 0;
+		for (size_t i = 0; i < h->faces.size(); i++) if (h->faces[i].axis != axis) do_rim = 1;
+		dim3 grid(nw > 0 ? 2 : 1, nf);
 		LaunchScope ls(h, "halo_xrim", s);
-		if (h->dtype == LBM_F32) halo_xrim_flag_kernel<float><<<grid, 256, 0, s>>>(A, W, (int)nw, h->wait_timeout_ns, h->d_error);
-		else halo_xrim_flag_kernel<double><<<grid, 256, 0, s>>>(A, W, (int)nw, h->wait_timeout_ns, h->d_error);
+		if (h->dtype == LBM_F32) halo_xrim_flag_kernel<float><<<grid, 1024, 0, s>>>(A, W, (int)nw, do_rim, h->wait_timeout_ns, h->d_error);
+		else halo_xrim_flag_kernel<double><<<grid, 1024, 0, s>>>(A, W, (int)nw, do_rim, h->wait_timeout_ns, h->d_error);
 	}
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;

@@ -71,7 +71,10 @@ struct StepParams {
 	T *xstage[2];
 	const T *xpull[2];
 	long long xface_n;       /* sy * sz: cells of an x face = stride between staging positions */
-	int bpr;                 /* > 0: full rows and sx is a multiple of the cells of a block -> blocks per row */
+	int bpr;                 /* blocks per row.  XFUSE launches require full rows that are a whole number of
+	                            blocks (sx % (blockDim * VEC) == 0, box = whole rows): the cell next to the low
+	                            face is then held by a fixed thread of the first block of a row, the one next to
+	                            the high face by a fixed thread of the last block -- no per-thread division */
 };
 
 /* slots an x face ships, ascending = their position in the staging block.
@@ -469,56 +472,49 @@ __device__ __forceinline__ int box_z(const StepParams<T> &P)
 
 /* thread -> first cell of its VEC-wide group inside the iteration box; false = out of box */
 template <typename T, int VEC>
-__device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid, long long &off)
+__device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
 {
 	const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
 	if (t >= (long long)P.nx * P.ny) return false;
+	long long off;
 	if (P.nx == P.sx) off = (long long)P.y0 * P.sx + t;
 	else { const int iy = (int)(t / P.nx), ix = (int)(t - (long long)iy * P.nx); off = (long long)(P.y0 + iy) * P.sx + P.x0 + ix; }
 	gid = (long long)box_z(P) * P.sxy + off;
 	return true;
 }
-template <typename T, int VEC>
-__device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
-{
-	long long off;
-	return box_cell<T, VEC>(P, gid, off);
-}
 
-/* XFUSE: is one cell of this thread's VEC-wide group the cell next to the low (side 0) / high (side 1)
- * x ghost face?  Returns the side (-1: no), the element and the cell's index in the face [z][y].
- * (sx >= 2 * VEC + 2 is required, so a thread never holds both.)  off = offset of the group inside its
- * plane.  Cheap (block-uniform division) when rows are whole multiples of a block; re-evaluated at each
- * use instead of being kept in registers across the collision (the volatile read of %ctaid defeats CSE). */
+/* XFUSE lanes (StepParams::bpr): does this thread hold the cell next to the low / high x ghost face,
+ * which element of its group is it, and the cell's index in the face [z][y].  Everything but the
+ * comparison with threadIdx is block-uniform. */
+template <int VEC> struct XLane {
+	enum { T_LO = VEC == 1 ? 1 : 0,            /* thread of the first block of a row holding x = 1 */
+	       E_LO = VEC == 1 ? 0 : 1,            /* ... and the element of its group */
+	       T_HI_BACK = VEC == 1 ? 1 : 0,       /* x = sx-2: thread blockDim-1-T_HI_BACK of the last block */
+	       E_HI = VEC == 1 ? 0 : VEC - 2 };
+};
 template <typename T, int VEC>
-__device__ __forceinline__ int xfuse_lane(const StepParams<T> &P, long long off, int &e, long long &rowidx)
+__device__ __forceinline__ bool x_is_lo(const StepParams<T> &P)
 {
-	unsigned int y;
-	int x0;
-	if (P.bpr > 0) {
-		unsigned int bx;
-		asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bx));
-		const unsigned int q = bx / (unsigned int)P.bpr;
-		y = (unsigned int)P.y0 + q;
-		x0 = (int)((bx - q * (unsigned int)P.bpr) * blockDim.x + threadIdx.x) * VEC;
-	} else {
-		const unsigned int po = (unsigned int)off;             /* a plane has < 2^32 cells */
-		y = po / (unsigned int)P.sx;
-		x0 = (int)(po - y * (unsigned int)P.sx);
-	}
-	rowidx = (long long)box_z(P) * P.sy + y;
-	if (x0 <= 1 && 1 < x0 + VEC) { e = 1 - x0; return 0; }
-	if (x0 <= P.sx - 2 && P.sx - 2 < x0 + VEC) { e = P.sx - 2 - x0; return 1; }
-	e = -1;
-	return -1;
+	return threadIdx.x == (unsigned int)XLane<VEC>::T_LO && (P.bpr == 1 || blockIdx.x % (unsigned int)P.bpr == 0u);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ bool x_is_hi(const StepParams<T> &P)
+{
+	return threadIdx.x == blockDim.x - 1u - (unsigned int)XLane<VEC>::T_HI_BACK
+		&& (P.bpr == 1 || blockIdx.x % (unsigned int)P.bpr == (unsigned int)P.bpr - 1u);
+}
+template <typename T>
+__device__ __forceinline__ int x_rowidx(const StepParams<T> &P)
+{
+	return box_z(P) * P.sy + P.y0 + (int)(P.bpr == 1 ? blockIdx.x : blockIdx.x / (unsigned int)P.bpr);   /* a face has < 2^31 cells */
 }
 
 /* ================================================================== ALPHA kernel */
 template <typename T, int VEC, bool SMAG, bool STORE, bool XFUSE>
 __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 {
-	long long gid, poff;
-	if (!box_cell<T, VEC>(P, gid, poff)) return;
+	long long gid;
+	if (!box_cell<T, VEC>(P, gid)) return;
 
 	int flag[VEC];
 	FlagIO<VEC>::load(P.flags + gid, flag);
@@ -531,41 +527,34 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 	/* XFUSE PULL, issued first so that it overlaps the 19 slot loads: what the x neighbour's beta step
 	 * streamed into the cell next to the face sits in my receive block (the reference's
 	 * setDensityDistribution(..., norm) would have scattered it into these slots) */
-	T px[5] = { 0, 0, 0, 0, 0 };
-	int pside = -1, pe = -1;
-	if (XFUSE) {
-		long long rowidx;
-		const int side = xfuse_lane<T, VEC>(P, poff, pe, rowidx);
-		if (side >= 0 && P.xpull[side]) {
-			const T *st = P.xpull[side] + rowidx;
-			pside = side;
+	const bool lo = XFUSE && x_is_lo<T, VEC>(P), hi = XFUSE && x_is_hi<T, VEC>(P);
+	T px[5];                                     /* only read when pulled */
+	bool pulled = false;
+	if (XFUSE && (lo || hi)) {
+		const T *st = lo ? P.xpull[0] : P.xpull[1];
+		if (st) {
+			st += x_rowidx(P);
+			pulled = true;
 #pragma unroll
-			for (int k = 0; k < 5; k++) px[k] = __ldcg(st + k * P.xface_n);
+			for (int k = 0; k < 5; k++) px[k] = __ldcg(st + k * (int)P.xface_n);      /* 5 * face cells < 2^31 (host) */
 		}
-		/* lbm_alpha.cl:31-32: ghost cells are skipped; obstacle cells write nothing (:305-343).  A group
-		 * that holds the cell next to an x face still pulls / ships that cell's slots. */
-		const bool xlane = side >= 0 && (P.xpull[side] || P.xstage[side]);
-		if (all_ghost && !xlane) return;
-		if (!any_write && !STORE && !xlane) return;
-	} else {
-		if (all_ghost) return;
-		if (!any_write && !STORE) return;
 	}
+	/* lbm_alpha.cl:31-32: ghost cells are skipped; obstacle cells write nothing (:305-343).  A group
+	 * that holds the cell next to an x face still pulls / ships that cell's slots. */
+	const bool xlane = XFUSE && ((lo && (P.xpull[0] || P.xstage[0])) || (hi && (P.xpull[1] || P.xstage[1])));
+	if (all_ghost && !xlane) return;
+	if (!any_write && !STORE && !xlane) return;
 
 	T v[19][VEC];
 	T *base = P.dd + gid;
 #pragma unroll
 	for (int i = 0; i < 19; i++) VecIO<T, VEC>::load(base + (long long)i * P.ns, v[i]);
 
-	const bool pulled = XFUSE && pside >= 0;
-	if (XFUSE && pside >= 0) {
+	if (XFUSE && pulled) {
 #pragma unroll
-		for (int e = 0; e < VEC; e++) if (e == pe) {
-#pragma unroll
-			for (int k = 0; k < 5; k++) {
-				if (pside == 0) v[2 * k + (k ? 2 : 0)][e] = px[k];     /* low face: slots 0,4,6,8,10 */
-				else v[2 * k + (k ? 3 : 1)][e] = px[k];                /* high face: slots 1,5,7,9,11 */
-			}
+		for (int k = 0; k < 5; k++) {
+			if (lo) v[2 * k + (k ? 2 : 0)][XLane<VEC>::E_LO] = px[k];       /* low face: slots 0,4,6,8,10 */
+			else v[2 * k + (k ? 3 : 1)][XLane<VEC>::E_HI] = px[k];          /* high face: slots 1,5,7,9,11 */
 		}
 	}
 
@@ -592,21 +581,17 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 		for (int i = 0; i < 18; i++) VecIO<T, VEC>::store(base + (long long)i * P.ns, v[i ^ 1]);
 		VecIO<T, VEC>::store(base + 18LL * P.ns, v[18]);
 	}
-	if (XFUSE) {
+	if (XFUSE && (lo || hi)) {
 		/* PUSH: slot j holds v[j^1] after this step.  Ghost cells (rims of the y/z faces) are left to
 		 * the rim pass that follows the y/z unpack (halo_xrim_flag_kernel). */
-		int e1;
-		long long rowidx;
-		const int side = xfuse_lane<T, VEC>(P, poff, e1, rowidx);
-		if (side >= 0 && P.xstage[side]) {
-			T *st = P.xstage[side] + rowidx;
+		T *st = lo ? P.xstage[0] : P.xstage[1];
+		const int xflag = lo ? flag[XLane<VEC>::E_LO] : flag[XLane<VEC>::E_HI];
+		if (st && xflag != FLAG_GHOST) {
+			st += x_rowidx(P);
 #pragma unroll
-			for (int e = 0; e < VEC; e++) if (e == e1 && flag[e] != FLAG_GHOST) {
-#pragma unroll
-				for (int k = 0; k < 5; k++)
-					st[k * P.xface_n] = side == 0 ? v[2 * k + (k ? 3 : 1)][e]      /* slots 0,4,6,8,10 <- v[1,5,7,9,11] */
-					                              : v[2 * k + (k ? 2 : 0)][e];     /* slots 1,5,7,9,11 <- v[0,4,6,8,10] */
-			}
+			for (int k = 0; k < 5; k++)
+				st[k * (int)P.xface_n] = lo ? v[2 * k + (k ? 3 : 1)][XLane<VEC>::E_LO]      /* slots 0,4,6,8,10 <- v[1,5,7,9,11] */
+				                            : v[2 * k + (k ? 2 : 0)][XLane<VEC>::E_HI];     /* slots 1,5,7,9,11 <- v[0,4,6,8,10] */
 		}
 	}
 	if (STORE) {
@@ -665,8 +650,8 @@ __device__ __forceinline__ constexpr bool beta_uses_offset_table()
 template <typename T, int VEC, bool SMAG, bool STORE, int ORDER, bool XFUSE>
 __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 {
-	long long gid, poff;
-	if (!box_cell<T, VEC>(P, gid, poff)) return;
+	long long gid;
+	if (!box_cell<T, VEC>(P, gid)) return;
 	if (beta_block_is_general<T, VEC>(P)) return;
 
 	const long long DY = P.sx, DZ = P.sxy;
@@ -674,20 +659,21 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	 * column next to the x = 1 (x = sx-2) cell holds what the neighbour's alpha step left there -- it sits
 	 * in my receive block at face index row(c) + e_y + e_z * sy (in range: this path is a plane + a row
 	 * away from the array ends); it is read as d[j^1]. */
-	T px[5] = { 0, 0, 0, 0, 0 };
-	int pside = -1, pe = -1;
-	if (XFUSE) {
-		long long rowidx;
-		const int side = xfuse_lane<T, VEC>(P, poff, pe, rowidx);
-		if (side >= 0 && P.xpull[side]) {
-			const T *st = P.xpull[side] + rowidx;
-			const long long sgn = side == 0 ? 1 : -1;          /* e_y, e_z of the high face's slots are mirrored */
-			pside = side;
-			px[0] = __ldcg(st);                                     /* slot 1 (-1, 0, 0) | slot 0 ( 1, 0, 0) */
-			px[1] = __ldcg(st + 1 * P.xface_n - sgn);               /* slot 5 (-1,-1, 0) | slot 4 ( 1, 1, 0) */
-			px[2] = __ldcg(st + 2 * P.xface_n + sgn);               /* slot 7 (-1, 1, 0) | slot 6 ( 1,-1, 0) */
-			px[3] = __ldcg(st + 3 * P.xface_n - sgn * P.sy);        /* slot 9 (-1, 0,-1) | slot 8 ( 1, 0, 1) */
-			px[4] = __ldcg(st + 4 * P.xface_n + sgn * P.sy);        /* slot 11 (-1, 0, 1) | slot 10 ( 1, 0,-1) */
+	const bool lo = XFUSE && x_is_lo<T, VEC>(P), hi = XFUSE && x_is_hi<T, VEC>(P);
+	T px[5];                                     /* only read when pulled */
+	bool pulled = false;
+	if (XFUSE && (lo || hi)) {
+		const T *st = lo ? P.xpull[0] : P.xpull[1];
+		if (st) {
+			st += x_rowidx(P);
+			const int sgn = lo ? 1 : -1;                       /* e_y, e_z of the high face's slots are mirrored */
+			const int fn = (int)P.xface_n;                     /* 5 * face cells < 2^31 (host) */
+			pulled = true;
+			px[0] = __ldcg(st);                                /* slot 1 (-1, 0, 0) | slot 0 ( 1, 0, 0) */
+			px[1] = __ldcg(st + (1 * fn - sgn));               /* slot 5 (-1,-1, 0) | slot 4 ( 1, 1, 0) */
+			px[2] = __ldcg(st + (2 * fn + sgn));               /* slot 7 (-1, 1, 0) | slot 6 ( 1,-1, 0) */
+			px[3] = __ldcg(st + (3 * fn - sgn * P.sy));        /* slot 9 (-1, 0,-1) | slot 8 ( 1, 0, 1) */
+			px[4] = __ldcg(st + (4 * fn + sgn * P.sy));        /* slot 11 (-1, 0, 1) | slot 10 ( 1, 0,-1) */
 		}
 	}
 	int flag[VEC];
@@ -722,14 +708,11 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	}
 	VecIO<T, VEC>::load(base + 18LL * P.ns, v[18]);
 
-	if (XFUSE && pside >= 0) {
+	if (XFUSE && pulled) {
 #pragma unroll
-		for (int e = 0; e < VEC; e++) if (e == pe) {
-#pragma unroll
-			for (int k = 0; k < 5; k++) {
-				if (pside == 0) v[2 * k + (k ? 2 : 0)][e] = px[k];     /* read as d[j^1], j = 1,5,7,9,11 */
-				else v[2 * k + (k ? 3 : 1)][e] = px[k];                /* j = 0,4,6,8,10 */
-			}
+		for (int k = 0; k < 5; k++) {
+			if (lo) v[2 * k + (k ? 2 : 0)][XLane<VEC>::E_LO] = px[k];       /* read as d[j^1], j = 1,5,7,9,11 */
+			else v[2 * k + (k ? 3 : 1)][XLane<VEC>::E_HI] = px[k];          /* j = 0,4,6,8,10 */
 		}
 	}
 
@@ -751,23 +734,19 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	}
 	VecIO<T, VEC>::store(base + 18LL * P.ns, v[18]);
 
-	if (XFUSE) {
+	if (XFUSE && (lo || hi)) {
 		/* PUSH: the x = 1 (x = sx-2) cell is the only writer of the e_x = -1 (+1) slots of the ghost
 		 * column next to it; the same values go to the neighbour, same face index as above. */
-		int e1;
-		long long rowidx;
-		const int side = xfuse_lane<T, VEC>(P, poff, e1, rowidx);
-		if (side >= 0 && P.xstage[side]) {
-			T *st = P.xstage[side] + rowidx;
-			const long long sgn = side == 0 ? 1 : -1;
-#pragma unroll
-			for (int e = 0; e < VEC; e++) if (e == e1) {
-				st[0] = side == 0 ? v[1][e] : v[0][e];
-				st[1 * P.xface_n - sgn] = side == 0 ? v[5][e] : v[4][e];
-				st[2 * P.xface_n + sgn] = side == 0 ? v[7][e] : v[6][e];
-				st[3 * P.xface_n - sgn * P.sy] = side == 0 ? v[9][e] : v[8][e];
-				st[4 * P.xface_n + sgn * P.sy] = side == 0 ? v[11][e] : v[10][e];
-			}
+		T *st = lo ? P.xstage[0] : P.xstage[1];
+		if (st) {
+			st += x_rowidx(P);
+			const int sgn = lo ? 1 : -1;
+			const int fn = (int)P.xface_n;
+			st[0] = lo ? v[1][XLane<VEC>::E_LO] : v[0][XLane<VEC>::E_HI];
+			st[1 * fn - sgn] = lo ? v[5][XLane<VEC>::E_LO] : v[4][XLane<VEC>::E_HI];
+			st[2 * fn + sgn] = lo ? v[7][XLane<VEC>::E_LO] : v[6][XLane<VEC>::E_HI];
+			st[3 * fn - sgn * P.sy] = lo ? v[9][XLane<VEC>::E_LO] : v[8][XLane<VEC>::E_HI];
+			st[4 * fn + sgn * P.sy] = lo ? v[11][XLane<VEC>::E_LO] : v[10][XLane<VEC>::E_HI];
 		}
 	}
 
@@ -788,11 +767,11 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 template <typename T, int VEC, bool SMAG, bool STORE, int ORDER, bool XFUSE>
 __global__ void lbm_beta_general_kernel(const StepParams<T> P)
 {
-	long long gid, poff;
-	if (!box_cell<T, VEC>(P, gid, poff)) return;
+	long long gid;
+	if (!box_cell<T, VEC>(P, gid)) return;
 	if (!beta_block_is_general<T, VEC>(P)) return;
 	const long long DY = P.sx, DZ = P.sxy;
-	const int gx0 = XFUSE ? (int)((unsigned int)poff % (unsigned int)P.sx) : 0;
+	const int gx0 = XFUSE ? (int)(gid % P.sx) : 0;
 #pragma unroll 1
 	for (int e = 0; e < VEC; e++) {
 		const long long c = gid + e;
@@ -1038,6 +1017,17 @@ __global__ void halo_push_kernel(const HaloAxis A)
 	halo_publish(F);
 }
 
+__device__ __forceinline__ unsigned int ld_acquire_sys(const volatile unsigned int *p)
+{
+	unsigned int v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(volatile unsigned int *p, unsigned int v)
+{
+	asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
 /* wait until the neighbour's push has raised my flag to the next sequence number (acquire at system
  * scope).  The expected number is counted in device memory.  A neighbour that never arrives (crashed
  * rank) must not hang the GPU: after timeout_ns the wait gives up and leaves a mark the host finds
@@ -1049,8 +1039,8 @@ __device__ __forceinline__ void halo_wait_face(const HaloFace &F, unsigned long 
 	unsigned long long t0 = 0;
 	unsigned int spins = 0;
 	/* sequence numbers only grow; signed distance tolerates wrap-around */
-	while ((int)(*F.flag - seq) < 0) {
-		__nanosleep(40);
+	while ((int)(ld_acquire_sys(F.flag) - seq) < 0) {
+		__nanosleep(20);
 		if ((++spins & 1023u) == 0) {
 			unsigned long long now;
 			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -1058,7 +1048,6 @@ __device__ __forceinline__ void halo_wait_face(const HaloFace &F, unsigned long 
 			else if (now - t0 > timeout_ns) { atomicExch(error_word, 1u); break; }
 		}
 	}
-	__threadfence_system();
 }
 
 /* x faces whose bulk went out of the step kernels (XFUSE): the rim pass.  The cells of an x face that lie
@@ -1066,36 +1055,48 @@ __device__ __forceinline__ void halo_wait_face(const HaloFace &F, unsigned long 
  * populations on their way to the diagonal neighbour) or are ghost cells the step kernel skipped; they
  * are re-read from dd -- final by now: this kernel runs behind the step kernels and the y/z unpack -- and
  * stored over whatever the step kernel sent for them.  Then the flag goes up.  F.origin[0] = column.
- * nwait > 0: one thread per face then waits for the neighbour's flag in the same launch (W = my receive
- * side): the whole exposed x tail of a step is this one small kernel. */
+ * ONE block per face (blockIdx.y) does that: no block counter, one release.  do_rim == 0 (no y/z
+ * neighbours, nothing to forward): the flag only.
+ * nwait > 0: blockIdx.x == 1 of each face is a one-thread waiter for the neighbour's flag (W = my
+ * receive side), running NEXT TO the rim pass: the whole exposed x tail of a step is this one launch. */
 template <typename T>
-__global__ void halo_xrim_flag_kernel(const HaloAxis A, const HaloAxis W, int nwait,
+__global__ void halo_xrim_flag_kernel(const HaloAxis A, const HaloAxis W, int nwait, int do_rim,
 		unsigned long long timeout_ns, unsigned int *error_word)
 {
-	const HaloFace &F = A.f[blockIdx.y];
-	const int sy = F.size[1], sz = F.size[2];
-	const unsigned int line_cells = 4u * (unsigned int)(sy + sz);
-	const unsigned int total = line_cells * (unsigned int)F.ncomp;
-	const T *dd = (const T *)F.dd;
-	T *st = (T *)F.staging;
-	for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-		const unsigned int c = t / line_cells, q = t - c * line_cells;
-		int y, z;
-		if (q < 4u * (unsigned int)sz) {                       /* rows y = 0, 1, sy-2, sy-1 */
-			const int w = (int)(q / (unsigned int)sz); z = (int)(q - (unsigned int)w * sz);
-			y = w < 2 ? w : sy - 4 + w;
-		} else {                                               /* rows z = 0, 1, sz-2, sz-1 */
-			const unsigned int r = q - 4u * (unsigned int)sz;
-			const int w = (int)(r / (unsigned int)sy); y = (int)(r - (unsigned int)w * sy);
-			z = w < 2 ? w : sz - 4 + w;
-		}
-		if (y < 0 || y >= sy || z < 0 || z >= sz) continue;    /* faces thinner than 4 */
-		const long long face = (long long)z * sy + y;
-		st[(long long)F.st_comp[c] * sy * sz + face] =
-			dd[(long long)F.dd_comp[c] * F.dd_stride + F.origin[0] + (long long)y * F.ss[0] + (long long)z * F.ss[0] * F.ss[1]];
+	if (blockIdx.x == 1) {
+		if (threadIdx.x == 0 && (int)blockIdx.y < nwait) halo_wait_face(W.f[blockIdx.y], timeout_ns, error_word);
+		return;
 	}
-	halo_publish(F);
-	if (blockIdx.x == 0 && (int)blockIdx.y < nwait && threadIdx.x == 64) halo_wait_face(W.f[blockIdx.y], timeout_ns, error_word);
+	const HaloFace &F = A.f[blockIdx.y];
+	unsigned int seq = 0;
+	if (threadIdx.x == 0) { seq = *F.sync_count + 1u; *F.sync_count = seq; }
+	if (do_rim) {
+		const int sy = F.size[1], sz = F.size[2];
+		const unsigned int line_cells = 4u * (unsigned int)(sy + sz);
+		const unsigned int total = line_cells * (unsigned int)F.ncomp;
+		const T *dd = (const T *)F.dd;
+		T *st = (T *)F.staging;
+		for (unsigned int t = threadIdx.x; t < total; t += blockDim.x) {
+			const unsigned int c = t / line_cells, q = t - c * line_cells;
+			int y, z;
+			if (q < 4u * (unsigned int)sz) {                       /* rows y = 0, 1, sy-2, sy-1 */
+				const int w = (int)(q / (unsigned int)sz); z = (int)(q - (unsigned int)w * sz);
+				y = w < 2 ? w : sy - 4 + w;
+			} else {                                               /* rows z = 0, 1, sz-2, sz-1 */
+				const unsigned int r = q - 4u * (unsigned int)sz;
+				const int w = (int)(r / (unsigned int)sy); y = (int)(r - (unsigned int)w * sy);
+				z = w < 2 ? w : sz - 4 + w;
+			}
+			if (y < 0 || y >= sy || z < 0 || z >= sz) continue;    /* faces thinner than 4 */
+			const long long face = (long long)z * sy + y;
+			st[(long long)F.st_comp[c] * sy * sz + face] =
+				dd[(long long)F.dd_comp[c] * F.dd_stride + F.origin[0] + (long long)y * F.ss[0] + (long long)z * F.ss[0] * F.ss[1]];
+		}
+	}
+	__syncthreads();
+	/* release at system scope, cumulative over the block's stores (barrier) and over the step kernels'
+	 * peer stores (stream order) */
+	if (threadIdx.x == 0) st_release_sys(F.flag, seq);
 }
 
 /* wait: ONE thread per face (not a grid of spinning blocks next to the step kernel) */
