@@ -603,9 +603,10 @@ def main():
                          "bit for bit against the CPU oracle; its verdict is the `parity` key of the JSON line)")
     ap.add_argument("--store", action="store_true", help="STORE_VELOCITY/STORE_DENSITY instantiations (visualisation/validate builds)")
     args = ap.parse_args()
-    if args.config:
+    if args.config:     # a preset fills in what the command line left at its default
         for k, v in PRESETS[args.config].items():
-            setattr(args, k, v)
+            if not hasattr(args, k) or getattr(args, k) == ap.get_default(k):
+                setattr(args, k, v)
     # The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner
     # under NCCL_DEBUG=VERSION, OpenMP/torch warnings): keep the real stdout for the result line and
     # point file descriptor 1 at stderr for everything else.

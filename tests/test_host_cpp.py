@@ -18,6 +18,8 @@ from turbulent_lbm_multigpu_b200.domain import CDomain
 from turbulent_lbm_multigpu_b200.host import build as host_build
 from turbulent_lbm_multigpu_b200.skeleton import compute_parameters
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 CONF = """<?xml version="1.0" encoding="ISO-8859-1"?>
 <lbm-configuration>
   <!-- physics -->
@@ -185,3 +187,47 @@ def test_cpp_known_answer_checksum(exe):
     out = run(exe, "-S", 64, "-l", 100, "-v")
     m = re.search(r"Checksum: ([-\d.]+)", out)
     assert m and abs(float(m.group(1)) - 20745.41210938) < 1e-6, out[-800:]
+
+
+@pytest.fixture(scope="module")
+def ipc_exe(tmp_path_factory):
+    """tests/cpp/ipc_ranks.cpp: one PROCESS per sub-domain (fork + socketpair carrying the 64-byte CUDA-IPC
+    handles), C ABI only -- the C/C++ multi-process transport a reference maintainer with MPI would write."""
+    libdir = os.path.join(ROOT, "turbulent_lbm_multigpu_b200", "lib")
+    exe = str(tmp_path_factory.mktemp("ipc") / "ipc_ranks")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-Wall", "-Wextra",
+                           os.path.join(ROOT, "tests", "cpp", "ipc_ranks.cpp"), "-o", exe, "-L" + libdir, "-llbm_b200",
+                           "-Wl,-rpath," + libdir, "-ldl", "-lrt", "-pthread"])
+    return exe
+
+
+def test_ipc_ranks_builds_and_fails_loudly_without_a_gpu(ipc_exe):
+    """no CUDA device: every rank reports it, the parent reports the failed ranks -- no CPU fallback, no hang"""
+    if _have_gpu():
+        pytest.skip("a CUDA device is present")
+    p = subprocess.run([ipc_exe, "32", "16", "16", "2", "1", "1", "4"], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 1 and "no CUDA device" in p.stderr and "validation: not run (2 ranks failed)" in p.stdout
+
+
+def _have_gpu():
+    import ctypes
+    from turbulent_lbm_multigpu_b200 import capi
+    n = ctypes.c_int(0)
+    return capi.load().lbmGetDeviceCount(ctypes.byref(n)) == 0 and n.value > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [
+    "32 16 16 2 1 1 40",                  # the reference's default split (x), x,y,z phase order
+    "32 16 16 2 1 1 41 zyx",              # ... x faces after the step kernel
+    "16 16 24 1 1 2 40 0.1",              # z-slabs, Smagorinsky
+    "768 16 16 2 1 1 20 zyx 0.1",         # rows of 384 cells: fused x exchange inside the vectorised step kernels
+    "32 32 24 1 2 2 21 0.1 double",       # pencils, fp64
+    "24 24 24 2 2 2 21 zyx 0.1",          # blocks: eight processes
+])
+def test_ipc_ranks_validate_criterion(ipc_exe, args):
+    """fork()ed ranks + CUDA IPC + lbmCommStep; the reference's validate criterion (src/main.cpp:309-408):
+    every rank's interior velocity block equals the single domain of size D - 2 (n - 1) bit for bit."""
+    p = subprocess.run([ipc_exe] + args.split(), capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, (p.stdout[-1500:], p.stderr[-1500:])
+    assert "validation: 0 failed cells" in p.stdout

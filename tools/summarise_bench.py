@@ -3,8 +3,8 @@
 import json
 import sys
 
-print("| file | N | workload | MLUPS | ms/step | roofline frac per GPU | halo exposed | e2e MLUPS |")
-print("|---|---|---|---|---|---|---|---|")
+print("| file | N | workload | MLUPS | ms/step | roofline frac per GPU | halo exposed | e2e MLUPS | parity | graph |")
+print("|---|---|---|---|---|---|---|---|---|---|")
 for f in sys.argv[1:]:
     try:
         j = json.loads(open(f).read().strip().splitlines()[-1])
@@ -15,7 +15,10 @@ for f in sys.argv[1:]:
         continue
     h = j.get("halo") or {}
     c = j["config"]
-    print("| %s | %d | %s %s %s | %.0f | %.4f | %.3f | %s | %.0f |" % (
+    par = j.get("parity")
+    print("| %s | %d | %s %s %s | %.0f | %.4f | %.3f | %s | %.0f | %s | %s |" % (
         f.split("/")[-1], j["n_gpus"], c["workload"].split(" D3Q19")[0].replace("lid-driven cavity ", ""),
         "x".join(str(v) for v in c["subdomain_num"]), j["dtype"], j["value"], j["ms_per_step"], j["roofline"]["frac"],
-        ("%.1f %%" % (100 * h["exposed_frac"])) if h else "-", j["e2e"]["value"]))
+        ("%.1f %%" % (100 * h["exposed_frac"])) if h else "-", j["e2e"]["value"],
+        "-" if not par else ("ok" if par.get("ok") else "FAIL" if par.get("ok") is False else "n/a"),
+        "yes" if j.get("cuda_graph") else "no"))
