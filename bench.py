@@ -363,6 +363,8 @@ def run_gpu(args):
     np_dtype = np.float32 if args.dtype == "f32" else np.float64
     elem = np.dtype(np_dtype).itemsize
     bytes_per_lup = 2 * 19 * elem + 4           # 156 B fp32, 308 B fp64
+    if args.store:
+        bytes_per_lup += 4 * elem               # STORE_VELOCITY + STORE_DENSITY: 3 + 1 more values written per cell
     cfg = scenario(n, args.size, args.scaling, args.decomp, args.cs, getattr(args, "shape", None))
     domain = CDomain(-1, cfg.domain_size, (0, 0, 0), cfg.domain_length)
     backend = TorchDistributedBackend() if world > 1 else None
@@ -556,7 +558,7 @@ def run_gpu(args):
             "parity": parity,
             "sync_mode": args.sync if world > 1 else None, "axis_order": axis_order if world > 1 else None,
             "cuda_graph": graph is not None,
-            "kernel_config": s.config(),
+            "kernel_config": dict(s.config(), store_velocity_density=bool(args.store)),
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
