@@ -151,6 +151,13 @@ bool x_fusable(lbm_t h)
 	if (!h->xfuse || h->axis_order != LBM_AXIS_ORDER_ZYX) return false;
 	/* whole blocks per row (fixed lanes), one lane per thread, 32-bit face offsets */
 	if (h->sx % (h->block * h->vec) != 0 || h->sx < 2 * h->vec + 2 || 5LL * h->sy * h->sz >= 0x7fffffffLL) return false;
+	/* lane key = (block in row << 10) | thread; row of a block = blockIdx.x / blocks per row by a
+	 * multiply that is exact while blockIdx.x * blocks per row < 2^32 */
+	const long long bpr = h->sx / (h->block * h->vec);
+	if (h->block > 1024 || bpr > (1 << 20) || bpr * bpr * h->sy >= 0x100000000LL) return false;
+#if LBM_XFUSE_GRID3D
+	if (h->sy > 65535 || h->sz > 65535) return false;
+#endif
 	bool any = false;
 	for (size_t i = 0; i < h->faces.size(); i++) {
 		const lbm_face &f = h->faces[i];
@@ -168,9 +175,20 @@ StepParams<T> make_params(lbm_t h, const Box &b, bool alpha, bool xfuse)
 	P.xstage[0] = P.xstage[1] = NULL;
 	P.xpull[0] = P.xpull[1] = NULL;
 	P.xface_n = (long long)h->sy * h->sz;
+	{
+		const int fn = (int)P.xface_n;                          /* 5 * fn < 2^31: x_fusable */
+		const int dy[5] = { 0, -1, 1, 0, 0 }, dz[5] = { 0, 0, 0, -1, 1 };   /* (e_y, e_z) of the low lane's slots 1,5,7,9,11 */
+		for (int k = 0; k < 5; k++) {
+			P.xoff[0][k] = k * fn + dy[k] + dz[k] * h->sy;
+			P.xoff[1][k] = k * fn - dy[k] - dz[k] * h->sy;
+			P.xoff[2][k] = k * fn;
+		}
+	}
 	const int cells_per_block = h->block * h->vec;
-	P.bpr = (b.nx == h->sx && b.x0 == 0 && h->sx % cells_per_block == 0) ? h->sx / cells_per_block : 0;
-	if (P.bpr == 0) xfuse = false;           /* (the boxes of an XFUSE step are whole rows; belt and braces) */
+	P.xbpr = (unsigned)(h->sx / cells_per_block);           /* meaningful when sx % cells_per_block == 0 (XFUSE launches) */
+	if (P.xbpr < 1) P.xbpr = 1;
+	P.xmagic = P.xbpr == 1 ? 0u : (unsigned)((0x100000000ULL + P.xbpr - 1) / P.xbpr);
+	P.xkey_hi = ((P.xbpr - 1) << 10) | (unsigned)(h->block - 1 - (h->vec == 1 ? 1 : 0));
 	if (xfuse) {
 		const int kind = alpha ? LBM_SYNC_ALPHA : LBM_SYNC_BETA;          /* the sync this step feeds */
 		const int consumed = alpha ? LBM_SYNC_BETA : LBM_SYNC_ALPHA;      /* the sync this step consumes */
@@ -238,7 +256,7 @@ void launch_beta(lbm_t h, const StepParams<T> &P, dim3 grid, dim3 block, cudaStr
 		if (nlo > 0) { Q.z0 = ranges[0][0]; Q.zsplit = nlo; Q.zjump = ranges[1][0] - (ranges[0][0] + nlo); }
 		else { Q.z0 = ranges[1][0]; Q.zsplit = 0x7fffffff; Q.zjump = 0; }
 		Q.nz = nlo + nhi;
-		dim3 g2(grid.x, (unsigned)Q.nz);
+		const dim3 g2 = (XPUSH && LBM_XFUSE_GRID3D) ? dim3(grid.x, grid.y, (unsigned)Q.nz) : dim3(grid.x, (unsigned)Q.nz);
 		/* with the quirk live this launch IS the whole beta step */
 		LaunchScope ls(h, P.wg > 0 ? "lbm_kernel_beta" : "lbm_kernel_beta.wrap", sg);
 		if (shipped) lbm_beta_general_kernel<T, VEC, SMAG, STORE, 0, XPUSH><<<g2, block, 0, sg>>>(Q);
@@ -257,10 +275,15 @@ template <typename T, int VEC>
 int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream_t sg, bool xpush)
 {
 	if (b.nx <= 0 || b.ny <= 0 || b.nz + b.nzb <= 0) return LBM_OK;
+	/* the fused x exchange needs whole rows that are a whole number of blocks (x_fusable; the boxes of a
+	 * z,y,x step are whole rows) */
+	if (xpush && !(b.nx == h->sx && b.x0 == 0 && h->sx % (h->block * VEC) == 0)) xpush = false;
 	const StepParams<T> P = make_params<T>(h, b, alpha, xpush);
 	const long long groups = ((long long)b.nx * b.ny) / VEC;
 	dim3 block(h->block);
-	dim3 grid((unsigned)((groups + h->block - 1) / h->block), (unsigned)(b.nz + b.nzb));
+	/* (blocks of a plane of the box, z rows); XFUSE launches (LBM_XFUSE_GRID3D): (blocks of a row, rows, z rows) */
+	const dim3 grid = (xpush && LBM_XFUSE_GRID3D) ? dim3((unsigned)(h->sx / (h->block * VEC)), (unsigned)b.ny, (unsigned)(b.nz + b.nzb))
+	                        : dim3((unsigned)((groups + h->block - 1) / h->block), (unsigned)(b.nz + b.nzb));
 	const bool store = h->desc.store_velocity || h->desc.store_density;
 #define LBM_DISPATCH(FN, XP)                                          \
 	do {                                                              \
@@ -1116,10 +1139,17 @@ int axis_push(lbm_t h, int kind, int axis, cudaStream_t s, bool exposed, bool ri
 		/* rim lines only exist where a y or z face has a neighbour (forwarded edges, ghost rims) */
 		int do_rim = 0;
 		for (size_t i = 0; i < h->faces.size(); i++) if (h->faces[i].axis != axis) do_rim = 1;
-		dim3 grid(nw > 0 ? 2 : 1, nf);
+		/* one rim element per thread: 4 * (Sy + Sz) cells x 5 slots per face */
+		int rim_blocks = 1;
+		if (do_rim) {
+			const long long elems = 4LL * (h->sy + h->sz) * 5;
+			rim_blocks = (int)((elems + 255) / 256);
+			if (rim_blocks > 128) rim_blocks = 128;
+		}
+		dim3 grid((unsigned)(rim_blocks + (nw > 0 ? 1 : 0)), nf);
 		LaunchScope ls(h, "halo_xrim", s);
-		if (h->dtype == LBM_F32) halo_xrim_flag_kernel<float><<<grid, 1024, 0, s>>>(A, W, (int)nw, do_rim, h->wait_timeout_ns, h->d_error);
-		else halo_xrim_flag_kernel<double><<<grid, 1024, 0, s>>>(A, W, (int)nw, do_rim, h->wait_timeout_ns, h->d_error);
+		if (h->dtype == LBM_F32) halo_xrim_flag_kernel<float><<<grid, 256, 0, s>>>(A, W, (int)nw, rim_blocks, do_rim, h->wait_timeout_ns, h->d_error);
+		else halo_xrim_flag_kernel<double><<<grid, 256, 0, s>>>(A, W, (int)nw, rim_blocks, do_rim, h->wait_timeout_ns, h->d_error);
 	}
 	CUDA_TRY(h, cudaGetLastError());
 	return LBM_OK;

@@ -71,10 +71,18 @@ struct StepParams {
 	T *xstage[2];
 	const T *xpull[2];
 	long long xface_n;       /* sy * sz: cells of an x face = stride between staging positions */
-	int bpr;                 /* blocks per row.  XFUSE launches require full rows that are a whole number of
-	                            blocks (sx % (blockDim * VEC) == 0, box = whole rows): the cell next to the low
-	                            face is then held by a fixed thread of the first block of a row, the one next to
-	                            the high face by a fixed thread of the last block -- no per-thread division */
+	/* element offsets of the five positions of a receive / staging block, relative to the lane's face index:
+	 * [0] beta, low lane: k * xface_n + (0, -1, +1, -sy, +sy) -- position k holds the slot with
+	 * (e_y, e_z) = (0,0) (-1,0) (1,0) (0,-1) (0,1), and a beta lane reads / writes location c + e;
+	 * [1] beta, high lane (e_y, e_z mirrored); [2] alpha: k * xface_n */
+	int xoff[3][5];
+	/* XFUSE launches cover whole rows that are a whole number of blocks (sx % (blockDim * VEC) == 0): the
+	 * cell next to the low face is held by a fixed thread of the first block of a row, the one next to the
+	 * high face by a fixed thread of the last block.  Row of a block = blockIdx.x / xbpr, as a multiply
+	 * (xmagic = ceil(2^32 / xbpr), exact while blockIdx.x * xbpr < 2^32; 0 when xbpr == 1) -- block-uniform,
+	 * no division anywhere.
+	 * xkey_hi: x_key() of the high lane, ((xbpr - 1) << 10) | (blockDim - 1 - XLane::T_HI_BACK) */
+	unsigned int xbpr, xmagic, xkey_hi;
 };
 
 /* slots an x face ships, ascending = their position in the staging block.
@@ -463,58 +471,76 @@ __device__ __forceinline__ void beta_cell(T (&d)[19], int flag, const StepParams
 	}
 }
 
-template <typename T>
+/* LBM_XFUSE_GRID3D=1 (default): XFUSE launches use a 3-D grid (blocks of a row, rows of the box, z rows), so
+ * that a block's place in its row and the row's index come straight from blockIdx; 0: every launch is
+ * (blocks of a plane of the box, z rows) and the row comes from a multiply by StepParams::xmagic.
+ * Measured (profiles/r2/xfuse_lane_ab.md): the 3-D grid is 0.3-1 % of a step faster. */
+#ifndef LBM_XFUSE_GRID3D
+#define LBM_XFUSE_GRID3D 1
+#endif
+template <bool XG>
+__device__ __forceinline__ unsigned int plane_block()
+{
+	return XG ? blockIdx.y * gridDim.x + blockIdx.x : blockIdx.x;
+}
+
+template <typename T, bool XG>
 __device__ __forceinline__ int box_z(const StepParams<T> &P)
 {
-	const int row = (int)blockIdx.y;
+	const int row = (int)(XG ? blockIdx.z : blockIdx.y);
 	return P.z0 + row + (row >= P.zsplit ? P.zjump : 0);
 }
 
 /* thread -> first cell of its VEC-wide group inside the iteration box; false = out of box */
-template <typename T, int VEC>
+template <typename T, int VEC, bool XG>
 __device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
 {
-	const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+	const long long t = ((long long)plane_block<XG>() * blockDim.x + threadIdx.x) * VEC;
 	if (t >= (long long)P.nx * P.ny) return false;
 	long long off;
-	if (P.nx == P.sx) off = (long long)P.y0 * P.sx + t;
+	if (XG || P.nx == P.sx) off = (long long)P.y0 * P.sx + t;      /* XG boxes are whole rows */
 	else { const int iy = (int)(t / P.nx), ix = (int)(t - (long long)iy * P.nx); off = (long long)(P.y0 + iy) * P.sx + P.x0 + ix; }
-	gid = (long long)box_z(P) * P.sxy + off;
+	gid = (long long)box_z<T, XG>(P) * P.sxy + off;
 	return true;
 }
 
-/* XFUSE lanes (StepParams::bpr): does this thread hold the cell next to the low / high x ghost face,
- * which element of its group is it, and the cell's index in the face [z][y].  Everything but the
- * comparison with threadIdx is block-uniform. */
+/* XFUSE lanes.  Rows are whole blocks (gridDim.x per row): the cell next to the low x ghost face is held by a
+ * fixed thread of the first block of a row, the one next to the high face by a fixed thread of the last. */
 template <int VEC> struct XLane {
 	enum { T_LO = VEC == 1 ? 1 : 0,            /* thread of the first block of a row holding x = 1 */
 	       E_LO = VEC == 1 ? 0 : 1,            /* ... and the element of its group */
 	       T_HI_BACK = VEC == 1 ? 1 : 0,       /* x = sx-2: thread blockDim-1-T_HI_BACK of the last block */
 	       E_HI = VEC == 1 ? 0 : VEC - 2 };
 };
-template <typename T, int VEC>
-__device__ __forceinline__ bool x_is_lo(const StepParams<T> &P)
+/* row of this block inside the box (XFUSE launches: whole rows, xbpr blocks each) */
+template <typename T, bool XG>
+__device__ __forceinline__ unsigned int x_row(const StepParams<T> &P)
 {
-	return threadIdx.x == (unsigned int)XLane<VEC>::T_LO && (P.bpr == 1 || blockIdx.x % (unsigned int)P.bpr == 0u);
+	if (XG) return blockIdx.y;
+	return P.xmagic ? __umulhi(blockIdx.x, P.xmagic) : blockIdx.x;
 }
-template <typename T, int VEC>
-__device__ __forceinline__ bool x_is_hi(const StepParams<T> &P)
+/* (block in row, thread) as one word: the lanes are the threads whose key is XLane::T_LO (low face) or
+ * StepParams::xkey_hi (high face) */
+template <typename T, bool XG>
+__device__ __forceinline__ unsigned int x_key(const StepParams<T> &P)
 {
-	return threadIdx.x == blockDim.x - 1u - (unsigned int)XLane<VEC>::T_HI_BACK
-		&& (P.bpr == 1 || blockIdx.x % (unsigned int)P.bpr == (unsigned int)P.bpr - 1u);
+	const unsigned int in_row = XG ? blockIdx.x : blockIdx.x - x_row<T, XG>(P) * P.xbpr;
+	return (in_row << 10) | threadIdx.x;
 }
-template <typename T>
-__device__ __forceinline__ int x_rowidx(const StepParams<T> &P)
+/* index of the lane's cell in the x face [z][y] (a face has < 2^31 cells) */
+template <typename T, bool XG>
+__device__ __forceinline__ int x_faceidx(const StepParams<T> &P)
 {
-	return box_z(P) * P.sy + P.y0 + (int)(P.bpr == 1 ? blockIdx.x : blockIdx.x / (unsigned int)P.bpr);   /* a face has < 2^31 cells */
+	return box_z<T, XG>(P) * P.sy + P.y0 + (int)x_row<T, XG>(P);
 }
 
 /* ================================================================== ALPHA kernel */
 template <typename T, int VEC, bool SMAG, bool STORE, bool XFUSE>
 __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 {
+	constexpr bool XG = XFUSE && LBM_XFUSE_GRID3D;
 	long long gid;
-	if (!box_cell<T, VEC>(P, gid)) return;
+	if (!box_cell<T, VEC, XG>(P, gid)) return;
 
 	int flag[VEC];
 	FlagIO<VEC>::load(P.flags + gid, flag);
@@ -526,22 +552,26 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 	for (int e = 0; e < VEC; e++) all_ghost &= (flag[e] == FLAG_GHOST);
 	/* XFUSE PULL, issued first so that it overlaps the 19 slot loads: what the x neighbour's beta step
 	 * streamed into the cell next to the face sits in my receive block (the reference's
-	 * setDensityDistribution(..., norm) would have scattered it into these slots) */
-	const bool lo = XFUSE && x_is_lo<T, VEC>(P), hi = XFUSE && x_is_hi<T, VEC>(P);
+	 * setDensityDistribution(..., norm) would have scattered it into these slots).  Into registers of
+	 * their own: a second load into a slot's register would wait for the first (the scoreboard is per warp). */
+	const unsigned int key = XFUSE ? x_key<T, XG>(P) : 0u;
+	const bool lane = XFUSE && (key == (unsigned int)XLane<VEC>::T_LO || key == P.xkey_hi);
+	int side = 0;
 	T px[5];                                     /* only read when pulled */
-	bool pulled = false;
-	if (XFUSE && (lo || hi)) {
-		const T *st = lo ? P.xpull[0] : P.xpull[1];
+	bool pulled = false, xlane = false;
+	if (XFUSE && lane) {
+		side = key == P.xkey_hi ? 1 : 0;
+		const T *st = P.xpull[side];
+		xlane = st || P.xstage[side];
 		if (st) {
-			st += x_rowidx(P);
+			const int f = x_faceidx<T, XG>(P);                 /* f + offset < 5 * face cells < 2^31 (host) */
 			pulled = true;
 #pragma unroll
-			for (int k = 0; k < 5; k++) px[k] = __ldcg(st + k * (int)P.xface_n);      /* 5 * face cells < 2^31 (host) */
+			for (int k = 0; k < 5; k++) px[k] = __ldcg(st + (f + P.xoff[2][k]));
 		}
 	}
 	/* lbm_alpha.cl:31-32: ghost cells are skipped; obstacle cells write nothing (:305-343).  A group
 	 * that holds the cell next to an x face still pulls / ships that cell's slots. */
-	const bool xlane = XFUSE && ((lo && (P.xpull[0] || P.xstage[0])) || (hi && (P.xpull[1] || P.xstage[1])));
 	if (all_ghost && !xlane) return;
 	if (!any_write && !STORE && !xlane) return;
 
@@ -551,10 +581,12 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 	for (int i = 0; i < 19; i++) VecIO<T, VEC>::load(base + (long long)i * P.ns, v[i]);
 
 	if (XFUSE && pulled) {
+		if (side == 0) {
 #pragma unroll
-		for (int k = 0; k < 5; k++) {
-			if (lo) v[2 * k + (k ? 2 : 0)][XLane<VEC>::E_LO] = px[k];       /* low face: slots 0,4,6,8,10 */
-			else v[2 * k + (k ? 3 : 1)][XLane<VEC>::E_HI] = px[k];          /* high face: slots 1,5,7,9,11 */
+			for (int k = 0; k < 5; k++) v[2 * k + (k ? 2 : 0)][XLane<VEC>::E_LO] = px[k];       /* low face: slots 0,4,6,8,10 */
+		} else {
+#pragma unroll
+			for (int k = 0; k < 5; k++) v[2 * k + (k ? 3 : 1)][XLane<VEC>::E_HI] = px[k];       /* high face: slots 1,5,7,9,11 */
 		}
 	}
 
@@ -581,17 +613,20 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
 		for (int i = 0; i < 18; i++) VecIO<T, VEC>::store(base + (long long)i * P.ns, v[i ^ 1]);
 		VecIO<T, VEC>::store(base + 18LL * P.ns, v[18]);
 	}
-	if (XFUSE && (lo || hi)) {
+	if (XFUSE && lane) {
 		/* PUSH: slot j holds v[j^1] after this step.  Ghost cells (rims of the y/z faces) are left to
 		 * the rim pass that follows the y/z unpack (halo_xrim_flag_kernel). */
-		T *st = lo ? P.xstage[0] : P.xstage[1];
-		const int xflag = lo ? flag[XLane<VEC>::E_LO] : flag[XLane<VEC>::E_HI];
+		T *st = P.xstage[side];
+		const int xflag = side == 0 ? flag[XLane<VEC>::E_LO] : flag[XLane<VEC>::E_HI];
 		if (st && xflag != FLAG_GHOST) {
-			st += x_rowidx(P);
+			const int f = x_faceidx<T, XG>(P);
+			if (side == 0) {
 #pragma unroll
-			for (int k = 0; k < 5; k++)
-				st[k * (int)P.xface_n] = lo ? v[2 * k + (k ? 3 : 1)][XLane<VEC>::E_LO]      /* slots 0,4,6,8,10 <- v[1,5,7,9,11] */
-				                            : v[2 * k + (k ? 2 : 0)][XLane<VEC>::E_HI];     /* slots 1,5,7,9,11 <- v[0,4,6,8,10] */
+				for (int k = 0; k < 5; k++) st[f + P.xoff[2][k]] = v[2 * k + (k ? 3 : 1)][XLane<VEC>::E_LO];      /* slots 0,4,6,8,10 <- v[1,5,7,9,11] */
+			} else {
+#pragma unroll
+				for (int k = 0; k < 5; k++) st[f + P.xoff[2][k]] = v[2 * k + (k ? 2 : 0)][XLane<VEC>::E_HI];      /* slots 1,5,7,9,11 <- v[0,4,6,8,10] */
+			}
 		}
 	}
 	if (STORE) {
@@ -615,18 +650,18 @@ __global__ void LBM_LB_ALPHA lbm_alpha_kernel(const StepParams<T> P)
  *                            (wrap.h:112-127) and work-group x-shift; only the blocks the
  *                            fast kernel skipped do work (launched on the outer planes only).
  * Keeping them apart keeps the wrap bookkeeping out of the hot kernel's register budget. */
-template <typename T, int VEC>
+template <typename T, int VEC, bool XG>
 __device__ __forceinline__ bool beta_block_is_general(const StepParams<T> &P)
 {
 	if (P.wg > 0) return true;
-	const long long t0 = (long long)blockIdx.x * blockDim.x * VEC;
+	const long long t0 = (long long)plane_block<XG>() * blockDim.x * VEC;
 	long long t1 = t0 + (long long)blockDim.x * VEC - 1;
 	const long long tmax = (long long)P.nx * P.ny - 1;
 	if (t1 > tmax) t1 = tmax;
 	long long o0, o1;
-	if (P.nx == P.sx) { o0 = (long long)P.y0 * P.sx + t0; o1 = (long long)P.y0 * P.sx + t1; }
+	if (XG || P.nx == P.sx) { o0 = (long long)P.y0 * P.sx + t0; o1 = (long long)P.y0 * P.sx + t1; }
 	else { o0 = (long long)(P.y0 + t0 / P.nx) * P.sx; o1 = (long long)(P.y0 + t1 / P.nx) * P.sx + P.sx - 1; }
-	const long long zb = (long long)box_z(P) * P.sxy;
+	const long long zb = (long long)box_z<T, XG>(P) * P.sxy;
 	const long long reach = P.sxy + P.sx + 1;
 	return (zb + o0 < reach) || (zb + o1 + reach >= P.n);
 }
@@ -650,30 +685,35 @@ __device__ __forceinline__ constexpr bool beta_uses_offset_table()
 template <typename T, int VEC, bool SMAG, bool STORE, int ORDER, bool XFUSE>
 __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 {
+	constexpr bool XG = XFUSE && LBM_XFUSE_GRID3D;
 	long long gid;
-	if (!box_cell<T, VEC>(P, gid)) return;
-	if (beta_block_is_general<T, VEC>(P)) return;
+	if (!box_cell<T, VEC, XG>(P, gid)) return;
+	if (beta_block_is_general<T, VEC, XG>(P)) return;
 
 	const long long DY = P.sx, DZ = P.sxy;
 	/* XFUSE PULL, issued first so that it overlaps the slot loads: location (slot j, c + e_j) in the ghost
 	 * column next to the x = 1 (x = sx-2) cell holds what the neighbour's alpha step left there -- it sits
 	 * in my receive block at face index row(c) + e_y + e_z * sy (in range: this path is a plane + a row
-	 * away from the array ends); it is read as d[j^1]. */
-	const bool lo = XFUSE && x_is_lo<T, VEC>(P), hi = XFUSE && x_is_hi<T, VEC>(P);
+	 * away from the array ends); it is read as d[j^1].  Into registers of their own: a second load into a
+	 * slot's register would wait for the first (the scoreboard is per warp). */
+	const unsigned int key = XFUSE ? x_key<T, XG>(P) : 0u;
+	const bool lane = XFUSE && (key == (unsigned int)XLane<VEC>::T_LO || key == P.xkey_hi);
+	int side = 0;
 	T px[5];                                     /* only read when pulled */
 	bool pulled = false;
-	if (XFUSE && (lo || hi)) {
-		const T *st = lo ? P.xpull[0] : P.xpull[1];
+	if (XFUSE && lane) {
+		side = key == P.xkey_hi ? 1 : 0;
+		const T *st = P.xpull[side];
 		if (st) {
-			st += x_rowidx(P);
-			const int sgn = lo ? 1 : -1;                       /* e_y, e_z of the high face's slots are mirrored */
-			const int fn = (int)P.xface_n;                     /* 5 * face cells < 2^31 (host) */
+			const int f = x_faceidx<T, XG>(P);                 /* f + offset < 5 * face cells < 2^31 (host) */
 			pulled = true;
-			px[0] = __ldcg(st);                                /* slot 1 (-1, 0, 0) | slot 0 ( 1, 0, 0) */
-			px[1] = __ldcg(st + (1 * fn - sgn));               /* slot 5 (-1,-1, 0) | slot 4 ( 1, 1, 0) */
-			px[2] = __ldcg(st + (2 * fn + sgn));               /* slot 7 (-1, 1, 0) | slot 6 ( 1,-1, 0) */
-			px[3] = __ldcg(st + (3 * fn - sgn * P.sy));        /* slot 9 (-1, 0,-1) | slot 8 ( 1, 0, 1) */
-			px[4] = __ldcg(st + (4 * fn + sgn * P.sy));        /* slot 11 (-1, 0, 1) | slot 10 ( 1, 0,-1) */
+			if (side == 0) {                                   /* slots 1,5,7,9,11: (-1,0,0) (-1,-1,0) (-1,1,0) (-1,0,-1) (-1,0,1) */
+#pragma unroll
+				for (int k = 0; k < 5; k++) px[k] = __ldcg(st + (f + P.xoff[0][k]));
+			} else {                                           /* slots 0,4,6,8,10: mirrored */
+#pragma unroll
+				for (int k = 0; k < 5; k++) px[k] = __ldcg(st + (f + P.xoff[1][k]));
+			}
 		}
 	}
 	int flag[VEC];
@@ -709,10 +749,12 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	VecIO<T, VEC>::load(base + 18LL * P.ns, v[18]);
 
 	if (XFUSE && pulled) {
+		if (side == 0) {
 #pragma unroll
-		for (int k = 0; k < 5; k++) {
-			if (lo) v[2 * k + (k ? 2 : 0)][XLane<VEC>::E_LO] = px[k];       /* read as d[j^1], j = 1,5,7,9,11 */
-			else v[2 * k + (k ? 3 : 1)][XLane<VEC>::E_HI] = px[k];          /* j = 0,4,6,8,10 */
+			for (int k = 0; k < 5; k++) v[2 * k + (k ? 2 : 0)][XLane<VEC>::E_LO] = px[k];       /* read as d[j^1], j = 1,5,7,9,11 */
+		} else {
+#pragma unroll
+			for (int k = 0; k < 5; k++) v[2 * k + (k ? 3 : 1)][XLane<VEC>::E_HI] = px[k];       /* j = 0,4,6,8,10 */
 		}
 	}
 
@@ -734,19 +776,19 @@ __global__ void LBM_LB_BETA lbm_beta_kernel(const StepParams<T> P)
 	}
 	VecIO<T, VEC>::store(base + 18LL * P.ns, v[18]);
 
-	if (XFUSE && (lo || hi)) {
+	if (XFUSE && lane) {
 		/* PUSH: the x = 1 (x = sx-2) cell is the only writer of the e_x = -1 (+1) slots of the ghost
 		 * column next to it; the same values go to the neighbour, same face index as above. */
-		T *st = lo ? P.xstage[0] : P.xstage[1];
+		T *st = P.xstage[side];
 		if (st) {
-			st += x_rowidx(P);
-			const int sgn = lo ? 1 : -1;
-			const int fn = (int)P.xface_n;
-			st[0] = lo ? v[1][XLane<VEC>::E_LO] : v[0][XLane<VEC>::E_HI];
-			st[1 * fn - sgn] = lo ? v[5][XLane<VEC>::E_LO] : v[4][XLane<VEC>::E_HI];
-			st[2 * fn + sgn] = lo ? v[7][XLane<VEC>::E_LO] : v[6][XLane<VEC>::E_HI];
-			st[3 * fn - sgn * P.sy] = lo ? v[9][XLane<VEC>::E_LO] : v[8][XLane<VEC>::E_HI];
-			st[4 * fn + sgn * P.sy] = lo ? v[11][XLane<VEC>::E_LO] : v[10][XLane<VEC>::E_HI];
+			const int f = x_faceidx<T, XG>(P);
+			if (side == 0) {
+#pragma unroll
+				for (int k = 0; k < 5; k++) st[f + P.xoff[0][k]] = v[2 * k + (k ? 3 : 1)][XLane<VEC>::E_LO];      /* slots 1,5,7,9,11 */
+			} else {
+#pragma unroll
+				for (int k = 0; k < 5; k++) st[f + P.xoff[1][k]] = v[2 * k + (k ? 2 : 0)][XLane<VEC>::E_HI];      /* slots 0,4,6,8,10 */
+			}
 		}
 	}
 
@@ -768,8 +810,9 @@ template <typename T, int VEC, bool SMAG, bool STORE, int ORDER, bool XFUSE>
 __global__ void lbm_beta_general_kernel(const StepParams<T> P)
 {
 	long long gid;
-	if (!box_cell<T, VEC>(P, gid)) return;
-	if (!beta_block_is_general<T, VEC>(P)) return;
+	constexpr bool XG = XFUSE && LBM_XFUSE_GRID3D;
+	if (!box_cell<T, VEC, XG>(P, gid)) return;
+	if (!beta_block_is_general<T, VEC, XG>(P)) return;
 	const long long DY = P.sx, DZ = P.sxy;
 	const int gx0 = XFUSE ? (int)(gid % P.sx) : 0;
 #pragma unroll 1
@@ -1055,28 +1098,28 @@ __device__ __forceinline__ void halo_wait_face(const HaloFace &F, unsigned long 
  * populations on their way to the diagonal neighbour) or are ghost cells the step kernel skipped; they
  * are re-read from dd -- final by now: this kernel runs behind the step kernels and the y/z unpack -- and
  * stored over whatever the step kernel sent for them.  Then the flag goes up.  F.origin[0] = column.
- * ONE block per face (blockIdx.y) does that: no block counter, one release.  do_rim == 0 (no y/z
- * neighbours, nothing to forward): the flag only.
- * nwait > 0: blockIdx.x == 1 of each face is a one-thread waiter for the neighbour's flag (W = my
+ * blockIdx.y = face; blockIdx.x < rim_blocks: the rim lines, one element per thread (the kernel is the
+ * exposed tail of a step: every gather is a DRAM round trip, so they all go out at once); the block that
+ * finishes last counts the sync up and releases the flag.  do_rim == 0 (no y/z neighbours, nothing to
+ * forward; rim_blocks == 1): the flag only.
+ * nwait > 0: blockIdx.x == rim_blocks of each face is a one-thread waiter for the neighbour's flag (W = my
  * receive side), running NEXT TO the rim pass: the whole exposed x tail of a step is this one launch. */
 template <typename T>
-__global__ void halo_xrim_flag_kernel(const HaloAxis A, const HaloAxis W, int nwait, int do_rim,
+__global__ void halo_xrim_flag_kernel(const HaloAxis A, const HaloAxis W, int nwait, int rim_blocks, int do_rim,
 		unsigned long long timeout_ns, unsigned int *error_word)
 {
-	if (blockIdx.x == 1) {
+	if ((int)blockIdx.x == rim_blocks) {
 		if (threadIdx.x == 0 && (int)blockIdx.y < nwait) halo_wait_face(W.f[blockIdx.y], timeout_ns, error_word);
 		return;
 	}
 	const HaloFace &F = A.f[blockIdx.y];
-	unsigned int seq = 0;
-	if (threadIdx.x == 0) { seq = *F.sync_count + 1u; *F.sync_count = seq; }
 	if (do_rim) {
 		const int sy = F.size[1], sz = F.size[2];
 		const unsigned int line_cells = 4u * (unsigned int)(sy + sz);
 		const unsigned int total = line_cells * (unsigned int)F.ncomp;
 		const T *dd = (const T *)F.dd;
 		T *st = (T *)F.staging;
-		for (unsigned int t = threadIdx.x; t < total; t += blockDim.x) {
+		for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (unsigned int)rim_blocks * blockDim.x) {
 			const unsigned int c = t / line_cells, q = t - c * line_cells;
 			int y, z;
 			if (q < 4u * (unsigned int)sz) {                       /* rows y = 0, 1, sy-2, sy-1 */
@@ -1094,9 +1137,21 @@ __global__ void halo_xrim_flag_kernel(const HaloAxis A, const HaloAxis W, int nw
 		}
 	}
 	__syncthreads();
-	/* release at system scope, cumulative over the block's stores (barrier) and over the step kernels'
-	 * peer stores (stream order) */
-	if (threadIdx.x == 0) st_release_sys(F.flag, seq);
+	if (threadIdx.x == 0) {
+		bool last = true;
+		if (rim_blocks > 1) {
+			__threadfence_system();                  /* this block's peer stores (barrier) before its count */
+			last = atomicAdd(F.block_counter, 1u) == (unsigned int)rim_blocks - 1u;
+			if (last) { *F.block_counter = 0; __threadfence_system(); }      /* ready for the next sync of this face */
+		}
+		if (last) {
+			const unsigned int seq = *F.sync_count + 1u;
+			*F.sync_count = seq;
+			/* release at system scope, cumulative over the rim blocks' stores (counted above) and over
+			 * the step kernels' peer stores (stream order) */
+			st_release_sys(F.flag, seq);
+		}
+	}
 }
 
 /* wait: ONE thread per face (not a grid of spinning blocks next to the step kernel) */
