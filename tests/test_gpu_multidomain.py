@@ -117,6 +117,9 @@ def test_zyx_axis_order_x_faces_after_the_interior(D, nums, steps, overlap):
     ((512, 24, 12), (2, 2, 1), 20),
     ((1024, 10, 8), (2, 1, 1), 11),      # two blocks per row
     ((120, 24, 16), (3, 1, 1), 21),      # a rank with two x faces
+    ((600, 12, 10), (2, 1, 1), 15),      # rows of 300 cells: no block size divides a row, separate x kernels
+    ((768, 12, 10), (2, 1, 1), 15),      # rows of 384 cells: the fused launches run with 96-thread blocks (192 groups = 2 x 96)
+    ((900, 10, 8), (3, 1, 1), 11),       # rows of 300 cells, two x faces
 ])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("cs", [0.0, 0.1])
@@ -177,6 +180,30 @@ def test_fused_x_exchange_with_small_blocks(D, nums, steps, dtype):
         k = c.getSolver().config()
         assert k["vector_width"] == 2 and k["block_size"] == 32
         assert (k["wg_quirk"] == 0) == (128 % sim.sub_size[0] != 0)
+    sim.run(steps)
+    make, po = omulti.make_oracle_factory(D, nums, L, dtype=dtype, variant=0, smagorinsky_cs=0.1)
+    md = omulti.MultiDomain(D, nums, make, slots="minimal", axis_order=(2, 1, 0))
+    md.run(steps)
+    for r, ctrl in enumerate(sim.controllers):
+        assert bits_equal(ctrl.getSolver().storeDensityDistribution(), md.ranks[r]["solver"].dd), (r, "dd vs oracle")
+
+
+@pytest.mark.parametrize("D,nums,steps", [
+    ((96, 32, 32), (3, 1, 1), 21),       # rows of 32 cells in one 128-thread block, work-group quirk live, two x faces
+    ((64, 32, 32), (2, 2, 1), 20),       # ... with a y neighbour: rim lines
+    ((200, 12, 10), (2, 1, 1), 15),      # rows of 100 cells: 50 groups in one block of 64
+])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fused_x_exchange_any_row_length(D, nums, steps, dtype, monkeypatch):
+    """Default block size, rows that no block size divides: on request (LBM_B200_XFUSE=2; slower than the
+    separate x kernels there, so not the default) the fused launches pick the block size that leaves the
+    fewest idle threads and the last block of a row is partly empty."""
+    monkeypatch.setenv("LBM_B200_XFUSE", "2")
+    L = (0.1, 0.1, 0.1)
+    cfg = _cfg()
+    cfg.smagorinsky_constant = 0.1
+    sim = InProcessSimulation(CDomain(-1, D, (0, 0, 0), L), nums, transport="p2p", overlap=True, config=cfg,
+                              dtype=dtype, axis_order="zyx")
     sim.run(steps)
     make, po = omulti.make_oracle_factory(D, nums, L, dtype=dtype, variant=0, smagorinsky_cs=0.1)
     md = omulti.MultiDomain(D, nums, make, slots="minimal", axis_order=(2, 1, 0))

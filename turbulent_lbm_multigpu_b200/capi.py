@@ -10,6 +10,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # LBM_B200_LIB: tuning hook to load an alternative build of the SAME CUDA library
 LIB_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(HERE, "lib", "liblbm_b200.so")
+# Sub-domains that share one GPU (tests, InProcessSimulation) keep two streams each, and a flag wait of the
+# one-sided exchange spins until the neighbour's kernels have run: with the default of 8 hardware queues a
+# neighbour's stream can end up queued behind such a wait.  Read by CUDA when the context is created.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 LBM_OK = 0
 LBM_ERR_INVALID, LBM_ERR_CUDA, LBM_ERR_NO_DEVICE, LBM_ERR_TIMEOUT = 1, 2, 3, 4

@@ -50,7 +50,7 @@ struct lbm_solver {
 	int x_in_kernel;             /* 1 + sync kind whose x faces the last step kernels pushed themselves (XFUSE), 0 = none */
 	int x_pending;               /* 1 + sync kind whose x faces were received but not scattered into dd: the next
 	                                XFUSE step reads them out of the receive block; anything else flushes first */
-	int xfuse;                   /* fused x push allowed (LBM_B200_XFUSE=0 turns it off) */
+	int xfuse;                   /* fused x push: 0 off, 1 rows that a block size divides, 2 any row (LBM_B200_XFUSE) */
 	unsigned int *d_error;       /* device word: a halo wait gave up (neighbour never arrived) */
 	unsigned long long wait_timeout_ns;
 	int device;
@@ -145,18 +145,53 @@ struct LaunchScope {
 uint32_t popcount19(uint32_t m);
 int flush_x_pending(lbm_t h, cudaStream_t s);
 
+/* threads per block of the XFUSE launches (whole rows, 3-D grid): the configured size when a row is a whole
+ * number of such blocks, else the largest multiple of 32 (>= 64) below it that divides a row -- measured good:
+ * 384-cell rows in 96-thread blocks cost what 256- and 512-cell rows cost in 128-thread blocks.
+ * *exact = false: no such size.  Rows are then fused only on request (LBM_B200_XFUSE=2: the size that leaves the
+ * fewest idle threads, last block of a row partly empty): 288..320-cell rows in 160-thread blocks cost 16-25 % of
+ * a step against 12-13 % with the separate x push/pull kernels (profiles/r2/xfuse_row_lengths.md). */
+int x_block(lbm_t h, bool *exact = NULL)
+{
+	const int groups = h->sx / h->vec;
+	if (exact) *exact = true;
+	if (groups % h->block == 0) return h->block;
+#if LBM_XFUSE_GRID3D
+	for (int b = h->block - 32; b >= 64; b -= 32) if (groups % b == 0) return b;
+	if (exact) *exact = false;
+	int best = h->block;
+	long long best_idle = -1;
+	for (int b = 256; b >= 64; b -= 32) {
+		const long long idle = (long long)((groups + b - 1) / b) * b - groups;
+		if (best_idle < 0 || idle < best_idle || (idle == best_idle && std::abs(b - h->block) < std::abs(best - h->block))) {
+			best = b; best_idle = idle;
+		}
+	}
+	return best;
+#else
+	if (exact) *exact = false;
+	return h->block;
+#endif
+}
+
 /* fused x push: only with the z,y,x phase order, the 5-slot payload and every x face connected */
 bool x_fusable(lbm_t h)
 {
 	if (!h->xfuse || h->axis_order != LBM_AXIS_ORDER_ZYX) return false;
-	/* whole blocks per row (fixed lanes), one lane per thread, 32-bit face offsets */
-	if (h->sx % (h->block * h->vec) != 0 || h->sx < 2 * h->vec + 2 || 5LL * h->sy * h->sz >= 0x7fffffffLL) return false;
-	/* lane key = (block in row << 10) | thread; row of a block = blockIdx.x / blocks per row by a
-	 * multiply that is exact while blockIdx.x * blocks per row < 2^32 */
-	const long long bpr = h->sx / (h->block * h->vec);
-	if (h->block > 1024 || bpr > (1 << 20) || bpr * bpr * h->sy >= 0x100000000LL) return false;
+	/* one lane per thread (x = 1 and x = sx-2 in different groups), 32-bit face offsets */
+	if (h->sx % h->vec != 0 || h->sx < 2 * h->vec + 2 || 5LL * h->sy * h->sz >= 0x7fffffffLL) return false;
+	bool exact;
+	const int xb = x_block(h, &exact);
+	if (!exact && h->xfuse < 2) return false;                /* rows that no block size divides: on request only */
+	const long long bpr = (h->sx / h->vec + xb - 1) / xb;
+	/* lane key = (block in row << 10) | thread */
+	if (xb > 1024 || bpr > (1 << 20)) return false;
 #if LBM_XFUSE_GRID3D
-	if (h->sy > 65535 || h->sz > 65535) return false;
+	if (h->sy > 65535 || h->sz > 65535) return false;          /* grid (blocks of a row, rows, z rows) */
+#else
+	/* rows must be whole blocks; row of a block = blockIdx.x / blocks per row by a multiply that is exact
+	 * while blockIdx.x * blocks per row < 2^32 */
+	if ((h->sx / h->vec) % xb != 0 || bpr * bpr * h->sy >= 0x100000000LL) return false;
 #endif
 	bool any = false;
 	for (size_t i = 0; i < h->faces.size(); i++) {
@@ -184,11 +219,14 @@ StepParams<T> make_params(lbm_t h, const Box &b, bool alpha, bool xfuse)
 			P.xoff[2][k] = k * fn;
 		}
 	}
-	const int cells_per_block = h->block * h->vec;
-	P.xbpr = (unsigned)(h->sx / cells_per_block);           /* meaningful when sx % cells_per_block == 0 (XFUSE launches) */
-	if (P.xbpr < 1) P.xbpr = 1;
-	P.xmagic = P.xbpr == 1 ? 0u : (unsigned)((0x100000000ULL + P.xbpr - 1) / P.xbpr);
-	P.xkey_hi = ((P.xbpr - 1) << 10) | (unsigned)(h->block - 1 - (h->vec == 1 ? 1 : 0));
+	{
+		const int xb = x_block(h), groups = h->sx / h->vec;
+		const int g_hi = (h->sx - 2) / h->vec;                  /* group of the cell next to the high face */
+		P.xbpr = (unsigned)((groups + xb - 1) / xb);
+		if (P.xbpr < 1) P.xbpr = 1;
+		P.xmagic = P.xbpr == 1 ? 0u : (unsigned)((0x100000000ULL + P.xbpr - 1) / P.xbpr);
+		P.xkey_hi = ((unsigned)(g_hi / xb) << 10) | (unsigned)(g_hi % xb);
+	}
 	if (xfuse) {
 		const int kind = alpha ? LBM_SYNC_ALPHA : LBM_SYNC_BETA;          /* the sync this step feeds */
 		const int consumed = alpha ? LBM_SYNC_BETA : LBM_SYNC_ALPHA;      /* the sync this step consumes */
@@ -275,15 +313,15 @@ template <typename T, int VEC>
 int launch_step_tv(lbm_t h, bool alpha, const Box &b, cudaStream_t s, cudaStream_t sg, bool xpush)
 {
 	if (b.nx <= 0 || b.ny <= 0 || b.nz + b.nzb <= 0) return LBM_OK;
-	/* the fused x exchange needs whole rows that are a whole number of blocks (x_fusable; the boxes of a
-	 * z,y,x step are whole rows) */
-	if (xpush && !(b.nx == h->sx && b.x0 == 0 && h->sx % (h->block * VEC) == 0)) xpush = false;
+	/* the fused x exchange works on whole rows (the boxes of a z,y,x step are) */
+	if (xpush && !(b.nx == h->sx && b.x0 == 0)) xpush = false;
 	const StepParams<T> P = make_params<T>(h, b, alpha, xpush);
 	const long long groups = ((long long)b.nx * b.ny) / VEC;
-	dim3 block(h->block);
+	const int threads = xpush ? x_block(h) : h->block;
+	dim3 block(threads);
 	/* (blocks of a plane of the box, z rows); XFUSE launches (LBM_XFUSE_GRID3D): (blocks of a row, rows, z rows) */
-	const dim3 grid = (xpush && LBM_XFUSE_GRID3D) ? dim3((unsigned)(h->sx / (h->block * VEC)), (unsigned)b.ny, (unsigned)(b.nz + b.nzb))
-	                        : dim3((unsigned)((groups + h->block - 1) / h->block), (unsigned)(b.nz + b.nzb));
+	const dim3 grid = (xpush && LBM_XFUSE_GRID3D) ? dim3((unsigned)((h->sx / VEC + threads - 1) / threads), (unsigned)b.ny, (unsigned)(b.nz + b.nzb))
+	                        : dim3((unsigned)((groups + threads - 1) / threads), (unsigned)(b.nz + b.nzb));
 	const bool store = h->desc.store_velocity || h->desc.store_density;
 #define LBM_DISPATCH(FN, XP)                                          \
 	do {                                                              \
@@ -557,7 +595,7 @@ int lbmCreate(lbm_t *out, const lbm_desc *d)
 	if (const char *e = getenv("LBM_B200_XSHELL")) h->xshell = atoi(e) > 1 ? atoi(e) : 2;
 	h->x_in_kernel = 0; h->x_pending = 0; h->d_error = NULL;
 	h->xfuse = 1;
-	if (const char *e = getenv("LBM_B200_XFUSE")) h->xfuse = atoi(e) != 0;
+	if (const char *e = getenv("LBM_B200_XFUSE")) h->xfuse = atoi(e);      /* 0 off, 1 default, 2 also rows no block size divides */
 	h->wait_timeout_ns = 30ull * 1000000000ull;
 	if (const char *e = getenv("LBM_B200_WAIT_TIMEOUT_MS")) if (atoll(e) > 0) h->wait_timeout_ns = (unsigned long long)atoll(e) * 1000000ull;
 	h->axis_order = LBM_AXIS_ORDER_XYZ;

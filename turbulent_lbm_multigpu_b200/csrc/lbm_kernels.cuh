@@ -76,12 +76,12 @@ struct StepParams {
 	 * (e_y, e_z) = (0,0) (-1,0) (1,0) (0,-1) (0,1), and a beta lane reads / writes location c + e;
 	 * [1] beta, high lane (e_y, e_z mirrored); [2] alpha: k * xface_n */
 	int xoff[3][5];
-	/* XFUSE launches cover whole rows that are a whole number of blocks (sx % (blockDim * VEC) == 0): the
-	 * cell next to the low face is held by a fixed thread of the first block of a row, the one next to the
-	 * high face by a fixed thread of the last block.  Row of a block = blockIdx.x / xbpr, as a multiply
-	 * (xmagic = ceil(2^32 / xbpr), exact while blockIdx.x * xbpr < 2^32; 0 when xbpr == 1) -- block-uniform,
-	 * no division anywhere.
-	 * xkey_hi: x_key() of the high lane, ((xbpr - 1) << 10) | (blockDim - 1 - XLane::T_HI_BACK) */
+	/* XFUSE launches cover whole rows with a 3-D grid (blocks of a row, rows, z rows; the last block of a row
+	 * may be partly empty): a block's place in its row and the row's index come straight from blockIdx.
+	 * xkey_hi: x_key() of the thread that holds the cell next to the high x face (x = sx-2),
+	 * (block << 10) | thread of group (sx-2) / VEC.
+	 * LBM_XFUSE_GRID3D=0 (2-D grid, rows must be whole blocks): row of a block = blockIdx.x / xbpr as a
+	 * multiply, xmagic = ceil(2^32 / xbpr), exact while blockIdx.x * xbpr < 2^32; 0 when xbpr == 1. */
 	unsigned int xbpr, xmagic, xkey_hi;
 };
 
@@ -478,12 +478,6 @@ __device__ __forceinline__ void beta_cell(T (&d)[19], int flag, const StepParams
 #ifndef LBM_XFUSE_GRID3D
 #define LBM_XFUSE_GRID3D 1
 #endif
-template <bool XG>
-__device__ __forceinline__ unsigned int plane_block()
-{
-	return XG ? blockIdx.y * gridDim.x + blockIdx.x : blockIdx.x;
-}
-
 template <typename T, bool XG>
 __device__ __forceinline__ int box_z(const StepParams<T> &P)
 {
@@ -495,21 +489,28 @@ __device__ __forceinline__ int box_z(const StepParams<T> &P)
 template <typename T, int VEC, bool XG>
 __device__ __forceinline__ bool box_cell(const StepParams<T> &P, long long &gid)
 {
-	const long long t = ((long long)plane_block<XG>() * blockDim.x + threadIdx.x) * VEC;
+	if (XG) {
+		/* whole rows, gridDim.x blocks each (the last one may be partly empty) */
+		const unsigned int x = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+		if (x >= (unsigned int)P.sx) return false;
+		gid = (long long)box_z<T, XG>(P) * P.sxy + (long long)(P.y0 + (int)blockIdx.y) * P.sx + x;
+		return true;
+	}
+	const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
 	if (t >= (long long)P.nx * P.ny) return false;
 	long long off;
-	if (XG || P.nx == P.sx) off = (long long)P.y0 * P.sx + t;      /* XG boxes are whole rows */
+	if (P.nx == P.sx) off = (long long)P.y0 * P.sx + t;
 	else { const int iy = (int)(t / P.nx), ix = (int)(t - (long long)iy * P.nx); off = (long long)(P.y0 + iy) * P.sx + P.x0 + ix; }
 	gid = (long long)box_z<T, XG>(P) * P.sxy + off;
 	return true;
 }
 
-/* XFUSE lanes.  Rows are whole blocks (gridDim.x per row): the cell next to the low x ghost face is held by a
- * fixed thread of the first block of a row, the one next to the high face by a fixed thread of the last. */
+/* XFUSE lanes: the cell next to the low x ghost face (x = 1) is element E_LO of group T_LO, held by thread T_LO
+ * of the first block of a row; the one next to the high face (x = sx-2) is element E_HI of group (sx-2) / VEC,
+ * a fixed thread of a fixed block of the row (StepParams::xkey_hi). */
 template <int VEC> struct XLane {
-	enum { T_LO = VEC == 1 ? 1 : 0,            /* thread of the first block of a row holding x = 1 */
-	       E_LO = VEC == 1 ? 0 : 1,            /* ... and the element of its group */
-	       T_HI_BACK = VEC == 1 ? 1 : 0,       /* x = sx-2: thread blockDim-1-T_HI_BACK of the last block */
+	enum { T_LO = VEC == 1 ? 1 : 0,
+	       E_LO = VEC == 1 ? 0 : 1,
 	       E_HI = VEC == 1 ? 0 : VEC - 2 };
 };
 /* row of this block inside the box (XFUSE launches: whole rows, xbpr blocks each) */
@@ -654,13 +655,21 @@ template <typename T, int VEC, bool XG>
 __device__ __forceinline__ bool beta_block_is_general(const StepParams<T> &P)
 {
 	if (P.wg > 0) return true;
-	const long long t0 = (long long)plane_block<XG>() * blockDim.x * VEC;
-	long long t1 = t0 + (long long)blockDim.x * VEC - 1;
-	const long long tmax = (long long)P.nx * P.ny - 1;
-	if (t1 > tmax) t1 = tmax;
-	long long o0, o1;
-	if (XG || P.nx == P.sx) { o0 = (long long)P.y0 * P.sx + t0; o1 = (long long)P.y0 * P.sx + t1; }
-	else { o0 = (long long)(P.y0 + t0 / P.nx) * P.sx; o1 = (long long)(P.y0 + t1 / P.nx) * P.sx + P.sx - 1; }
+	long long o0, o1;                            /* first and last cell of the block, inside its plane */
+	if (XG) {
+		const long long row = (long long)(P.y0 + (int)blockIdx.y) * P.sx;
+		const long long x0 = (long long)blockIdx.x * blockDim.x * VEC;
+		long long x1 = x0 + (long long)blockDim.x * VEC - 1;
+		if (x1 > P.sx - 1) x1 = P.sx - 1;
+		o0 = row + x0; o1 = row + x1;
+	} else {
+		const long long t0 = (long long)blockIdx.x * blockDim.x * VEC;
+		long long t1 = t0 + (long long)blockDim.x * VEC - 1;
+		const long long tmax = (long long)P.nx * P.ny - 1;
+		if (t1 > tmax) t1 = tmax;
+		if (P.nx == P.sx) { o0 = (long long)P.y0 * P.sx + t0; o1 = (long long)P.y0 * P.sx + t1; }
+		else { o0 = (long long)(P.y0 + t0 / P.nx) * P.sx; o1 = (long long)(P.y0 + t1 / P.nx) * P.sx + P.sx - 1; }
+	}
 	const long long zb = (long long)box_z<T, XG>(P) * P.sxy;
 	const long long reach = P.sxy + P.sx + 1;
 	return (zb + o0 < reach) || (zb + o1 + reach >= P.n);

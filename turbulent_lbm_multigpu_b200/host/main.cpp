@@ -215,6 +215,11 @@ static int run(CConfiguration<T> *cfg, const Options &opt)
 
 int main(int argc, char **argv)
 {
+	/* rank threads that share a GPU keep two streams each, and a flag wait of the one-sided exchange spins
+	 * until the neighbour's kernels have run: with the default of 8 hardware queues a neighbour's stream can end
+	 * up queued BEHIND such a wait (false dependency) and the run stalls until the wait times out.  Must be set
+	 * before the first CUDA call; an explicit setting of the user wins. */
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 	/* parsed into double, converted once into the simulation type */
 	int domain_size[3] = { 32, 32, 32 }, subdomain_nums[3] = { 1, 1, 1 };
 	double domain_length[3] = { 0.1, 0.1, 0.1 }, gravitation_y = -9.81, viscosity = 0.001308, timestep = -1.0, smagorinsky = 0.0;
