@@ -195,7 +195,9 @@ int lbmCommSync(lbm_t h, int sync_kind);                /* for each axis in orde
  *                       stores from registers, no strided gather afterwards); behind the step kernel
  *                       a small rim pass forwards the edge lines the y/z phases delivered and raises
  *                       the flag, then wait + unpack.  Use it when the decomposition cuts x.
- *                       (5-slot payload only; LBM_B200_XFUSE=0 falls back to a separate x push kernel.)
+ *                       (5-slot payload only, rows that are a whole number of thread blocks of 128 or
+ *                       of a smaller multiple of 32; otherwise, or with LBM_B200_XFUSE=0, the x faces go
+ *                       through separate push / wait / unpack kernels behind the step kernel.)
  * Every rank of a run must use the same order.  LBM_B200_AXIS_ORDER=xyz|zyx presets it. */
 #define LBM_AXIS_ORDER_XYZ 0
 #define LBM_AXIS_ORDER_ZYX 1
