@@ -10,6 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # many tests put several sub-domains (two streams each, spinning flag waits) on ONE GPU: more hardware
+    # queues than CUDA's default of 8, set before the first CUDA call of the session (capi.want_hardware_queues)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
 def _have_gpu():

@@ -161,6 +161,35 @@ def test_product_never_imports_the_oracle():
                 assert "liblbm_oracle" not in src and "libref" not in src, f
 
 
+def test_every_environment_switch_is_documented():
+    """Each LBM_B200_* variable the library, the hosts or bench.py read appears in INTEGRATION.md section 5."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    seen = set()
+    for base in ("turbulent_lbm_multigpu_b200", "bench.py"):
+        path = os.path.join(ROOT, base)
+        files = [path] if os.path.isfile(path) else [os.path.join(d, f) for d, _, fs in os.walk(path) for f in fs]
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                src = open(f, errors="replace").read()
+                seen.update(re.findall(r'(?:getenv\(|environ(?:\.get)?[\(\[])\s*"(LBM_B200_[A-Z_]+)"', src))
+    assert "LBM_B200_XFUSE" in seen and "LBM_B200_PROFILE" in seen
+    missing = sorted(v for v in seen if v not in doc)
+    assert not missing, missing
+
+
+def test_shared_gpu_runs_ask_for_more_hardware_queues(monkeypatch):
+    """capi.want_hardware_queues never overrides the user's setting and is not applied at import
+    (bench.py with one rank per GPU keeps CUDA's default)."""
+    monkeypatch.delenv("CUDA_DEVICE_MAX_CONNECTIONS", raising=False)
+    capi.want_hardware_queues()
+    assert os.environ["CUDA_DEVICE_MAX_CONNECTIONS"] == "32"
+    monkeypatch.setenv("CUDA_DEVICE_MAX_CONNECTIONS", "4")
+    capi.want_hardware_queues()
+    assert os.environ["CUDA_DEVICE_MAX_CONNECTIONS"] == "4"
+    src = open(os.path.join(ROOT, "turbulent_lbm_multigpu_b200", "capi.py")).read()
+    assert not re.search(r"^os\.environ", src, flags=re.M)
+
+
 def test_halo_slot_masks():
     lib = capi.load()
     m = ctypes.c_uint32()

@@ -10,10 +10,16 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # LBM_B200_LIB: tuning hook to load an alternative build of the SAME CUDA library
 LIB_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(HERE, "lib", "liblbm_b200.so")
-# Sub-domains that share one GPU (tests, InProcessSimulation) keep two streams each, and a flag wait of the
-# one-sided exchange spins until the neighbour's kernels have run: with the default of 8 hardware queues a
-# neighbour's stream can end up queued behind such a wait.  Read by CUDA when the context is created.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
+def want_hardware_queues(n=32):
+    """Sub-domains that SHARE one GPU (tests, InProcessSimulation with more sub-domains than GPUs) keep two
+    streams each, and a flag wait of the one-sided exchange spins until the neighbour's kernels have run: with
+    CUDA's default of 8 hardware queues a neighbour's stream can end up queued behind such a wait (reproduced,
+    profiles/r2/n1_pytest_host_cpp_8_hw_queues.log).  CUDA reads the variable when the context is created, so
+    this must run before the first CUDA call of the process; an explicit setting of the user wins.  Not needed --
+    and not touched -- with one rank per GPU (bench.py, torchrun)."""
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", str(n))
 
 LBM_OK = 0
 LBM_ERR_INVALID, LBM_ERR_CUDA, LBM_ERR_NO_DEVICE, LBM_ERR_TIMEOUT = 1, 2, 3, 4

@@ -434,6 +434,8 @@ class InProcessSimulation:
                  transport="copy", overlap=False, **controller_kw):
         self.nums = tuple(int(v) for v in subdomainNums)
         self.nranks = self.nums[0] * self.nums[1] * self.nums[2]
+        if transport == "p2p" and self.nranks > (len(set(devices)) if devices else 1):
+            capi.want_hardware_queues()     # sub-domains share a GPU (effective when CUDA is not initialised yet)
         self.slots = slots
         self.transport = transport      # "copy": one peer-copy kernel per face + host phase sync
         self.overlap = overlap          # "p2p": push/flag/pull faces, no host synchronisation
