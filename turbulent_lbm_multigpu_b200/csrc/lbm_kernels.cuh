@@ -4,9 +4,10 @@
  * What the kernels compute is defined by the reference's OpenCL kernels
  * (src/cl_programs/lbm_alpha.cl, lbm_beta.cl, lbm_init.cl, copy_buffer_rect.cl); HOW they
  * compute it is B200-first:
- *   - one thread owns VEC consecutive x cells (4 x fp32 / 2 x fp64 = 16 B): every slot whose
- *     lattice vector has e_x = 0 (all 19 in alpha, 9 of 19 in beta) moves as one 128-bit
- *     LDG/STG; the +-1 shifted slots of beta move as 32/64/32-bit pieces;
+ *   - one thread owns VEC consecutive x cells (shipped: 2 -> 64-bit LDG/STG; 4 x fp32 / 2 x fp64 = 16 B is
+ *     available and measured slower: registers): every slot whose lattice vector has e_x = 0 (all
+ *     19 in alpha, 9 of 19 in beta) moves as one vector LDG/STG; the +-1 shifted slots of beta move as
+ *     32-bit (VEC = 2) or 32/64/32-bit (VEC = 4) pieces;
  *   - no shared memory and no barriers: the reference's __local x-shift staging
  *     (lbm_beta.cl:167-234, 7 barriers) exists to align loads on 2010 hardware; here the
  *     L1/L2 absorb the one-element overlap between neighbouring threads and HBM traffic
