@@ -192,6 +192,7 @@ def test_fused_x_exchange_with_small_blocks(D, nums, steps, dtype):
     ((96, 32, 32), (3, 1, 1), 21),       # rows of 32 cells in one 128-thread block, work-group quirk live, two x faces
     ((64, 32, 32), (2, 2, 1), 20),       # ... with a y neighbour: rim lines
     ((200, 12, 10), (2, 1, 1), 15),      # rows of 100 cells: 50 groups in one block of 64
+    ((82, 12, 10), (2, 1, 1), 15),       # rows of 41 cells: one cell per thread, the lanes are threads 1 and 39
 ])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_fused_x_exchange_any_row_length(D, nums, steps, dtype, monkeypatch):
@@ -204,6 +205,27 @@ def test_fused_x_exchange_any_row_length(D, nums, steps, dtype, monkeypatch):
     cfg.smagorinsky_constant = 0.1
     sim = InProcessSimulation(CDomain(-1, D, (0, 0, 0), L), nums, transport="p2p", overlap=True, config=cfg,
                               dtype=dtype, axis_order="zyx")
+    sim.run(steps)
+    make, po = omulti.make_oracle_factory(D, nums, L, dtype=dtype, variant=0, smagorinsky_cs=0.1)
+    md = omulti.MultiDomain(D, nums, make, slots="minimal", axis_order=(2, 1, 0))
+    md.run(steps)
+    for r, ctrl in enumerate(sim.controllers):
+        assert bits_equal(ctrl.getSolver().storeDensityDistribution(), md.ranks[r]["solver"].dd), (r, "dd vs oracle")
+
+
+@pytest.mark.parametrize("D,nums,steps", [((512, 12, 10), (2, 1, 1), 15), ((768, 12, 10), (3, 1, 1), 11)])
+@pytest.mark.parametrize("dtype,vw", [(np.float32, 1), (np.float32, 4), (np.float64, 1)])
+def test_fused_x_exchange_other_vector_widths(D, nums, steps, dtype, vw):
+    """1 and 4 cells per thread (the shipped default is 2): the lanes sit in other threads / elements
+    (XLane), rows of 256 cells are 2 blocks of 128 one-cell threads or one block of 64 four-cell threads."""
+    L = (0.1, 0.1, 0.1)
+    cfg = _cfg()
+    cfg.smagorinsky_constant = 0.1
+    sim = InProcessSimulation(CDomain(-1, D, (0, 0, 0), L), nums, transport="p2p", overlap=True, config=cfg,
+                              dtype=dtype, axis_order="zyx", vector_width=vw)
+    for c in sim.controllers:
+        k = c.getSolver().config()
+        assert k["vector_width"] == vw and k["wg_quirk"] == 0
     sim.run(steps)
     make, po = omulti.make_oracle_factory(D, nums, L, dtype=dtype, variant=0, smagorinsky_cs=0.1)
     md = omulti.MultiDomain(D, nums, make, slots="minimal", axis_order=(2, 1, 0))
